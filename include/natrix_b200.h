@@ -1,0 +1,162 @@
+/* natrix_b200.h - C ABI of libnatrix_b200.so
+ *
+ * This is the drop-in boundary for ONE path of fbertola/Natrix: the per-step stable-fluids
+ * pipeline that natrix/core/fluid_simulator.py drives through bgfx-python.  Every entry
+ * point below replaces a group of bgfx calls made by the reference (cited as
+ * "ref: file:line", paths relative to the reference root).  Plain C types only: no
+ * torch, no C++ in the signatures; bind it with ctypes / cffi / cgo / JNI.
+ *
+ * Conventions
+ *   - every call returns 0 on success and a negative natrix_status on failure;
+ *     natrix_last_error() returns a thread-local, NUL-terminated description;
+ *   - handles are owned by the caller and released with natrix_destroy / natrix_dye_destroy
+ *     (ref: FluidSimulator.destroy, fluid_simulator.py:476-515);
+ *   - a handle is not thread-safe; calls are enqueued on the simulator's CUDA stream and
+ *     return before the GPU finishes (the reference is deferred too: bgfx.dispatch only
+ *     records, work runs at bgfx.frame()).  natrix_copy_out / natrix_sync / natrix_field_stats
+ *     synchronise;
+ *   - there is no CPU fallback: without a CUDA device every call fails with
+ *     NATRIX_ERR_CUDA.
+ *
+ * Layout of fields (row-major, idx = y*width + x, float32):
+ *   VELOCITY  float2 per cell (x, y)            8 B   ref: fluid_simulator.py:357-361
+ *   PRESSURE  float  per cell                   4 B   ref: :362-365 (scalar)
+ *   DIVERGENCE, VORTICITY  float per cell       4 B   ref: :366-367
+ *   OBSTACLES float2 per cell, (1,0)/(0,1)/0    8 B   ref: :368 (kept as 1 byte/cell in HBM;
+ *                                                     expanded on copy_out)
+ *   DYE       float  per dye cell               4 B   ref: demo/smooth_particles_area.py:158-162
+ */
+#ifndef NATRIX_B200_H
+#define NATRIX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct natrix_sim natrix_sim;
+typedef struct natrix_dye natrix_dye;
+
+enum natrix_status {
+    NATRIX_OK = 0,
+    NATRIX_ERR_ARG = -1,     /* bad argument (null handle, size mismatch, unknown id) */
+    NATRIX_ERR_CUDA = -2,    /* CUDA runtime / driver failure, message has the CUDA error */
+    NATRIX_ERR_STATE = -3,   /* call not valid in the current state */
+    NATRIX_ERR_RANGE = -4    /* a slab's halo was too small for this step (multi-GPU only) */
+};
+
+enum natrix_field {
+    NATRIX_VELOCITY = 0,
+    NATRIX_PRESSURE = 1,
+    NATRIX_DIVERGENCE = 2,
+    NATRIX_VORTICITY = 3,
+    NATRIX_OBSTACLES = 4,
+    NATRIX_NBMASK = 5        /* internal 4-bit blocked-neighbour mask, 1 byte per cell */
+};
+
+enum natrix_option {
+    NATRIX_OPT_PIPELINE = 0, /* 0 = one kernel per reference shader (reference dispatch order);
+                                1 = fused / temporally blocked kernels (default)            */
+    NATRIX_OPT_JACOBI_DEPTH = 1, /* sweeps per launch of the temporally blocked Jacobi kernel */
+    NATRIX_OPT_TIMING = 2,   /* 1 = record per-stage CUDA events (natrix_get_timings)        */
+    NATRIX_OPT_GRAPH = 3,    /* 1 = replay natrix_step through a captured CUDA graph          */
+    NATRIX_OPT_PACKED = 4    /* 1 = f32x2 packed arithmetic in the Jacobi kernel              */
+};
+
+/* ---- lifetime ------------------------------------------------------------------------
+ * ref: FluidSimulator.__init__ (fluid_simulator.py:37-48): createUniform x15,
+ * createProgram x12, createDynamicVertexBuffer x7 (shaders_utils.py:7-12), setBuffer
+ * slots 1-7.  All fields start at zero. */
+int natrix_create(int width, int height, int device, natrix_sim** out);
+
+/* One row slab of a taller global grid (multi-GPU, one process per GPU).  The slab owns
+ * global rows [row0, row0+rows) of a width x global_height grid and keeps `halo` extra
+ * rows above and below that the host fills by halo exchange (see natrix_halo_*). */
+int natrix_create_slab(int width, int global_height, int row0, int rows, int halo, int device,
+                       natrix_sim** out);
+int natrix_destroy(natrix_sim* sim);
+
+/* ---- parameters ------------------------------------------------------------------------
+ * ref: property setters fluid_simulator.py:58-111 and _update_params :315-336 (setUniform
+ * _Speed, _Dissipation, _VorticityScale, _Alpha, _rBeta).  viscosity is a double because the
+ * reference derives alpha = 1/viscosity and rBeta = 1/(4+alpha) in Python double before
+ * narrowing to c_float; viscosity == 0 skips the viscosity pass (:220). */
+int natrix_set_params(natrix_sim* sim, float speed, int iterations, float dissipation,
+                      float vorticity, double viscosity, int has_borders);
+int natrix_set_option(natrix_sim* sim, int option, int value);
+int natrix_get_option(natrix_sim* sim, int option, int* value);
+
+/* ---- impulses and obstacles ------------------------------------------------------------
+ * ref: add_velocity :116-131 (shader.AddVelocity.comp), add_circle_obstacle :135-153
+ * (shader.AddCircleObstacle.comp), add_triangle_obstacle :156-172
+ * (shader.AddTriangleObstacle.comp).  Positions are normalised [0,1]; radius in cells. */
+int natrix_add_velocity(natrix_sim* sim, float px, float py, float vx, float vy, float radius);
+int natrix_add_circle_obstacle(natrix_sim* sim, float px, float py, float radius, int is_static);
+int natrix_add_triangle_obstacle(natrix_sim* sim, float p1x, float p1y, float p2x, float p2y,
+                                 float p3x, float p3y, int is_static);
+
+/* ---- the hot path ----------------------------------------------------------------------
+ * ref: FluidSimulator.update :174-280: [InitBoundaries] -> AdvectVelocity -> CalcVorticity ->
+ * ApplyVorticity -> [Viscosity] -> Divergence -> clear pressure -> iterations x Poisson ->
+ * SubtractGradient -> clear obstacles.  For a slab this runs the whole step only when the
+ * slab is the full grid; multi-GPU hosts call the natrix_step_phase pieces with halo
+ * exchanges between them. */
+int natrix_step(natrix_sim* sim, float dt);
+
+/* Multi-GPU pieces of one step (slab handles).  Phases, in order:
+ *   0 advect (needs VELOCITY halo of natrix_halo_rows_needed(sim, 0, dt) rows)
+ *   1 vorticity+confinement(+viscosity)+divergence+mask (needs post-advect VELOCITY halo 4)
+ *   2 `sweeps` Jacobi sweeps (needs PRESSURE halo `sweeps`, DIVERGENCE+NBMASK halo `sweeps`)
+ *   3 subtract gradient + clear obstacles (needs PRESSURE halo 1)                         */
+int natrix_step_phase(natrix_sim* sim, int phase, float dt, int sweeps);
+int natrix_halo_rows_needed(natrix_sim* sim, int phase, float dt);
+/* Device addresses of the rows to send / to receive for one field:
+ * side 0 = towards lower row indices ("up"), 1 = towards higher ("down").
+ * send = the slab's own first/last `rows` rows; recv = the halo rows beyond them. */
+int natrix_halo_region(natrix_sim* sim, int field, int side, int rows, void** send_ptr,
+                       void** recv_ptr, size_t* bytes);
+
+/* ---- field access ------------------------------------------------------------------------
+ * The reference exposes only get_velocity_buffer() (:113-114, a bgfx handle) and has no host
+ * upload / readback at all.  natrix_field_ptr is the zero-copy equivalent of
+ * that handle (device pointer of the CURRENT read buffer; invalidated by the next mutating
+ * call); copy_in / copy_out / field_stats are additive extensions used by tests and viewers.
+ * For OBSTACLES copy_out/copy_in convert from/to the reference's float2 encoding. */
+int natrix_field_ptr(natrix_sim* sim, int field, void** dev_ptr, size_t* bytes);
+int natrix_copy_out(natrix_sim* sim, int field, void* host, size_t bytes);
+int natrix_copy_in(natrix_sim* sim, int field, const void* host, size_t bytes);
+/* out[0..3] = sum, sum of squares, min, max over all components (deterministic order). */
+int natrix_field_stats(natrix_sim* sim, int field, double* out4);
+
+/* ---- dye ("smooth particles area") ----------------------------------------------------
+ * ref: demo/smooth_particles_area.py:15-211, demo/shaders/shader.AddParticle.comp,
+ * shader.AdvectParticle.comp.  The dye grid may have a different resolution from the
+ * velocity grid; it reads the simulator's CURRENT velocity and obstacle buffers (the
+ * reference relies on the slot-1 / slot-7 bindings the simulator left behind). */
+int natrix_dye_create(natrix_sim* sim, int width, int height, natrix_dye** out);
+int natrix_dye_destroy(natrix_dye* dye);
+int natrix_dye_add(natrix_dye* dye, float px, float py, float radius, float strength);
+int natrix_dye_step(natrix_dye* dye, float dt, float speed, float dissipation);
+int natrix_dye_field_ptr(natrix_dye* dye, void** dev_ptr, size_t* bytes);
+int natrix_dye_copy_out(natrix_dye* dye, void* host, size_t bytes);
+int natrix_dye_copy_in(natrix_dye* dye, const void* host, size_t bytes);
+int natrix_dye_stats(natrix_dye* dye, double* out4);
+
+/* ---- synchronisation / introspection ------------------------------------------------- */
+int natrix_sync(natrix_sim* sim);
+/* CUDA stream the simulator enqueues on (a cudaStream_t), for event timing by the caller. */
+int natrix_stream(natrix_sim* sim, void** stream);
+/* Per-stage milliseconds of the last step when NATRIX_OPT_TIMING is on.  Index:
+ * 0 advect, 1 vorticity/confinement/viscosity, 2 divergence, 3 jacobi, 4 gradient, 5 clears. */
+int natrix_get_timings(natrix_sim* sim, float* ms, int n);
+/* Number of kernels (and memsets) this handle has launched since creation. */
+int natrix_launch_count(natrix_sim* sim, unsigned long long* kernels);
+const char* natrix_last_error(void);
+const char* natrix_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NATRIX_B200_H */

@@ -1,0 +1,699 @@
+// api.cu - the extern "C" boundary of libnatrix_b200.so (see include/natrix_b200.h) and the
+// orchestration of one simulation step (ref: FluidSimulator.update, fluid_simulator.py:174-280).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "jacobi_tb.h"
+
+using namespace natrix;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(expr)                                                                         \
+    do {                                                                                 \
+        cudaError_t e__ = (expr);                                                        \
+        if (e__ != cudaSuccess)                                                          \
+            return fail(NATRIX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+#define NEED(cond, msg) \
+    do { if (!(cond)) return fail(NATRIX_ERR_ARG, msg); } while (0)
+
+enum Stage { ST_ADVECT = 0, ST_VORT, ST_DIV, ST_JACOBI, ST_GRAD, ST_CLEAR, ST_COUNT };
+
+}  // namespace
+
+struct natrix_sim {
+    Geom g{};
+    int device = 0;
+    cudaStream_t st = nullptr;
+    size_t rows_alloc = 0, cells_alloc = 0;     // including halos
+    // allocations (base) and row-0 views
+    float2* vel_base[2] = {nullptr, nullptr};
+    float* p_base[2] = {nullptr, nullptr};
+    float *div_base = nullptr, *vort_base = nullptr;
+    uint8_t *obs_base = nullptr, *nbm_base = nullptr;
+    float2* vel[2] = {nullptr, nullptr};
+    float* p[2] = {nullptr, nullptr};
+    float *div = nullptr, *vort = nullptr;
+    uint8_t *obs = nullptr, *nbm = nullptr;
+    int vr = 0, pr = 0;                          // VELOCITY_READ / PRESSURE_READ indices
+    // parameters (fluid_simulator.py:28-35 defaults)
+    float speed = 500.0f, dissipation = 1.0f, vorticity = 0.0f;
+    float alpha = (float)(1.0 / 0.1), rbeta = (float)(1.0 / (4.0 + 1.0 / 0.1));
+    int iterations = 50, has_borders = 1, viscous = 1;
+    // options
+    int pipeline = 1, jacobi_depth = 8, timing = 0, graph = 0, packed = 1;
+    // bookkeeping
+    std::vector<SplatV> pending;                 // add_velocity calls not yet applied (pipeline 1)
+    bool obs_dirty = false, p_is_zero = false;
+    int* d_err = nullptr;
+    int* h_err = nullptr;
+    double *d_scratch = nullptr, *d_out4 = nullptr, *h_out4 = nullptr;
+    float2* d_tmp2 = nullptr;                    // staging for OBSTACLES copy in/out
+    unsigned long long launches = 0;
+    cudaEvent_t ev[ST_COUNT + 1] = {};
+    float stage_ms[ST_COUNT] = {};
+    JacobiTB* tb = nullptr;
+    std::vector<natrix_dye*> dyes;
+
+    int ext_lo(int k) const { int lo = -k; if (g.y0 + lo < 0) lo = -g.y0; return lo < -g.halo ? -g.halo : lo; }
+    int ext_hi(int k) const {
+        int hi = g.hl + k;
+        if (g.y0 + hi > g.hg) hi = g.hg - g.y0;
+        return hi > g.hl + g.halo ? g.hl + g.halo : hi;
+    }
+};
+
+struct natrix_dye {
+    natrix_sim* sim = nullptr;
+    int w = 0, h = 0;
+    float* d[2] = {nullptr, nullptr};
+    int rd = 0;
+    std::vector<SplatD> pending;
+};
+
+namespace {
+
+template <class T>
+cudaError_t alloc_rows(T** base, T** view, const natrix_sim* s) {
+    cudaError_t e = cudaMalloc((void**)base, s->cells_alloc * sizeof(T));
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(*base, 0, s->cells_alloc * sizeof(T), s->st);
+    *view = *base + (size_t)s->g.halo * s->g.w;
+    return e;
+}
+
+int select_device(const natrix_sim* s) {
+    CU(cudaSetDevice(s->device));
+    return 0;
+}
+
+void stamp(natrix_sim* s, int i) {
+    if (s->timing) cudaEventRecord(s->ev[i], s->st);
+}
+
+// apply queued add_velocity calls in one pass (pipeline 1) - identical per-cell arithmetic
+int flush_splats(natrix_sim* s) {
+    size_t i = 0;
+    while (i < s->pending.size()) {
+        SplatVBatch b;
+        b.n = 0;
+        while (i < s->pending.size() && b.n < MAX_SPLATS) b.s[b.n++] = s->pending[i++];
+        s->launches += launch_add_velocity(s->vel[s->vr], s->vel[1 - s->vr], s->g, s->ext_lo(s->g.halo),
+                                           s->ext_hi(s->g.halo), b, s->st);
+        s->vr = 1 - s->vr;
+    }
+    s->pending.clear();
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int flush_dye(natrix_dye* d) {
+    natrix_sim* s = d->sim;
+    size_t i = 0;
+    while (i < d->pending.size()) {
+        SplatDBatch b;
+        b.n = 0;
+        while (i < d->pending.size() && b.n < MAX_SPLATS) b.s[b.n++] = d->pending[i++];
+        s->launches += launch_dye_add(d->d[d->rd], d->d[1 - d->rd], d->w, d->h, b, s->st);
+        d->rd = 1 - d->rd;
+    }
+    d->pending.clear();
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int check_range_flag(natrix_sim* s) {
+    // only slabs can gather outside their rows; the full grid never sets the flag
+    if (s->g.hl == s->g.hg) return 0;
+    CU(cudaMemcpyAsync(s->h_err, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    if (*s->h_err) {
+        CU(cudaMemsetAsync(s->d_err, 0, sizeof(int), s->st));
+        return fail(NATRIX_ERR_RANGE, "advection back-trace left the slab's halo rows; enlarge halo");
+    }
+    return 0;
+}
+
+// ---- the four phases of a step -------------------------------------------------------------
+int phase_advect(natrix_sim* s, float dt) {
+    const Geom& g = s->g;
+    if (int rc = flush_splats(s)) return rc;
+    stamp(s, ST_ADVECT);
+    const bool fold = s->pipeline != 0 && s->has_borders;
+    if (s->has_borders && !fold)
+        s->launches += launch_init_boundaries(s->vel[s->vr], g, s->ext_lo(g.halo), s->ext_hi(g.halo), s->st);
+    s->launches += launch_advect(s->vel[s->vr], s->obs, s->vel[1 - s->vr], g, s->ext_lo(4), s->ext_hi(4), dt,
+                                 s->speed, s->dissipation, fold, s->d_err, s->st);
+    s->vr = 1 - s->vr;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int phase_forces(natrix_sim* s, float dt) {
+    const Geom& g = s->g;
+    stamp(s, ST_VORT);
+    s->launches += launch_vorticity(s->vel[s->vr], s->vort, g, s->ext_lo(3), s->ext_hi(3), s->st);
+    s->launches += launch_confinement(s->vel[s->vr], s->vort, s->vel[1 - s->vr], g, s->ext_lo(2), s->ext_hi(2),
+                                      dt, s->vorticity, s->st);
+    s->vr = 1 - s->vr;
+    if (s->viscous) {
+        s->launches += launch_viscosity(s->vel[s->vr], s->vel[1 - s->vr], g, s->ext_lo(1), s->ext_hi(1),
+                                        s->alpha, s->rbeta, s->st);
+        s->vr = 1 - s->vr;
+    }
+    stamp(s, ST_DIV);
+    s->launches += launch_divergence(s->vel[s->vr], s->obs, s->div, s->nbm, g, 0, g.hl, s->st);
+    // clear pressure (fluid_simulator.py:236-248); halo rows included so the first Jacobi
+    // block needs no exchange
+    CU(cudaMemsetAsync(s->p_base[s->pr], 0, s->cells_alloc * sizeof(float), s->st));
+    s->launches += 1;
+    s->p_is_zero = true;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// `sweeps` Jacobi sweeps; requires p, div, nbmask valid on ext(sweeps) (exchange done by caller)
+int phase_jacobi(natrix_sim* s, int sweeps) {
+    const Geom& g = s->g;
+    int left = sweeps;
+    while (left > 0) {
+        if (s->pipeline == 0) {
+            s->launches += launch_poisson_ref(s->p[s->pr], s->div, s->obs, s->p[1 - s->pr], g,
+                                              s->ext_lo(left - 1), s->ext_hi(left - 1), s->st);
+            s->pr = 1 - s->pr;
+            left -= 1;
+        } else if (!jacobi_tb_supported(g)) {
+            // widths TMA cannot address (not a multiple of 16, or narrower than one strip)
+            s->launches += launch_poisson_mask(s->p[s->pr], s->div, s->nbm, s->p[1 - s->pr], g,
+                                               s->ext_lo(left - 1), s->ext_hi(left - 1), s->st);
+            s->pr = 1 - s->pr;
+            left -= 1;
+        } else {
+            int t = left < s->jacobi_depth ? left : s->jacobi_depth;
+            int n = jacobi_tb_launch(s->tb, s->p[s->pr], s->div, s->nbm, s->p[1 - s->pr], g, t,
+                                     s->ext_lo(left - t), s->ext_hi(left - t), s->p_is_zero, s->packed, s->st);
+            if (n < 0) return fail(NATRIX_ERR_CUDA, std::string("jacobi_tb: ") + jacobi_tb_error(s->tb));
+            s->launches += n;
+            s->pr = 1 - s->pr;
+            left -= t;
+        }
+        s->p_is_zero = false;
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int phase_project(natrix_sim* s) {
+    const Geom& g = s->g;
+    stamp(s, ST_GRAD);
+    if (s->pipeline == 0)
+        s->launches += launch_gradient_ref(s->vel[s->vr], s->p[s->pr], s->obs, s->vel[1 - s->vr], g, 0, g.hl, s->st);
+    else
+        s->launches += launch_gradient_mask(s->vel[s->vr], s->p[s->pr], s->nbm, s->vel[1 - s->vr], g, 0, g.hl, s->st);
+    s->vr = 1 - s->vr;
+    stamp(s, ST_CLEAR);
+    // clear obstacles (fluid_simulator.py:268-280); skipped when nothing was stamped since the
+    // last clear (the map is already all zero)
+    if (s->obs_dirty || s->pipeline == 0) {
+        CU(cudaMemsetAsync(s->obs_base, 0, s->cells_alloc, s->st));
+        s->launches += 1;
+        s->obs_dirty = false;
+    }
+    stamp(s, ST_COUNT);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int field_info(natrix_sim* s, int field, void** base_row0, size_t* elem) {
+    switch (field) {
+    case NATRIX_VELOCITY: *base_row0 = s->vel[s->vr]; *elem = sizeof(float2); return 0;
+    case NATRIX_PRESSURE: *base_row0 = s->p[s->pr]; *elem = sizeof(float); return 0;
+    case NATRIX_DIVERGENCE: *base_row0 = s->div; *elem = sizeof(float); return 0;
+    case NATRIX_VORTICITY: *base_row0 = s->vort; *elem = sizeof(float); return 0;
+    case NATRIX_OBSTACLES: *base_row0 = s->obs; *elem = sizeof(uint8_t); return 0;
+    case NATRIX_NBMASK: *base_row0 = s->nbm; *elem = sizeof(uint8_t); return 0;
+    default: return fail(NATRIX_ERR_ARG, "unknown field id");
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* natrix_last_error(void) { return g_err.c_str(); }
+const char* natrix_version(void) { return "natrix_b200 0.1 (sm_100a)"; }
+
+int natrix_create_slab(int width, int global_height, int row0, int rows, int halo, int device,
+                       natrix_sim** out) {
+    NEED(out, "out is null");
+    *out = nullptr;
+    NEED(width > 0 && global_height > 0, "width and height must be positive");
+    NEED(rows > 0 && row0 >= 0 && row0 + rows <= global_height, "slab rows outside the global grid");
+    NEED(halo >= 0, "halo must be >= 0");
+    NEED(rows == global_height ? true : halo >= 1, "a partial slab needs halo >= 1");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(NATRIX_ERR_CUDA, "no such CUDA device");
+    CU(cudaSetDevice(device));
+    natrix_sim* s = new natrix_sim();
+    s->device = device;
+    s->g = Geom{width, global_height, row0, rows, halo};
+    s->rows_alloc = (size_t)rows + 2 * (size_t)halo;
+    s->cells_alloc = s->rows_alloc * (size_t)width;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = alloc_rows(&s->vel_base[i], &s->vel[i], s);
+        if (e == cudaSuccess) e = alloc_rows(&s->p_base[i], &s->p[i], s);
+    }
+    if (e == cudaSuccess) e = alloc_rows(&s->div_base, &s->div, s);
+    if (e == cudaSuccess) e = alloc_rows(&s->vort_base, &s->vort, s);
+    if (e == cudaSuccess) e = alloc_rows(&s->obs_base, &s->obs, s);
+    if (e == cudaSuccess) e = alloc_rows(&s->nbm_base, &s->nbm, s);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_err, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_err, 0, sizeof(int), s->st);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_err, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_scratch, 4 * 1024 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_out4, 4 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_out4, 4 * sizeof(double));
+    for (int i = 0; i <= ST_COUNT && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+    if (e != cudaSuccess) {
+        std::string msg = std::string("natrix_create: ") + cudaGetErrorString(e);
+        natrix_destroy(s);
+        return fail(NATRIX_ERR_CUDA, msg);
+    }
+    s->tb = jacobi_tb_create();
+    *out = s;
+    return 0;
+}
+
+int natrix_create(int width, int height, int device, natrix_sim** out) {
+    return natrix_create_slab(width, height, 0, height, 0, device, out);
+}
+
+int natrix_destroy(natrix_sim* s) {
+    if (!s) return 0;
+    cudaSetDevice(s->device);
+    if (s->st) cudaStreamSynchronize(s->st);
+    for (natrix_dye* d : s->dyes) d->sim = nullptr;   // orphaned dye handles stay destroyable
+    jacobi_tb_destroy(s->tb);
+    for (int i = 0; i < 2; ++i) { cudaFree(s->vel_base[i]); cudaFree(s->p_base[i]); }
+    cudaFree(s->div_base); cudaFree(s->vort_base); cudaFree(s->obs_base); cudaFree(s->nbm_base);
+    cudaFree(s->d_err); cudaFree(s->d_scratch); cudaFree(s->d_out4); cudaFree(s->d_tmp2);
+    if (s->h_err) cudaFreeHost(s->h_err);
+    if (s->h_out4) cudaFreeHost(s->h_out4);
+    for (int i = 0; i <= ST_COUNT; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->st) cudaStreamDestroy(s->st);
+    delete s;
+    return 0;
+}
+
+int natrix_set_params(natrix_sim* s, float speed, int iterations, float dissipation, float vorticity,
+                      double viscosity, int has_borders) {
+    NEED(s, "null simulator");
+    // same validation as the property setters (fluid_simulator.py:58-111)
+    NEED(speed > 0, "'Speed' should be greater than zero");
+    NEED(iterations > 0, "'Iterations' should be grater than zero");
+    NEED(dissipation > 0, "'Dissipation' should be grater than zero");
+    NEED(vorticity >= 0, "'Vorticity' should be grater or equal than zero");
+    NEED(viscosity >= 0.0, "'Viscosity' should be greater or equal than zero");
+    s->speed = speed; s->iterations = iterations; s->dissipation = dissipation;
+    s->vorticity = vorticity; s->has_borders = has_borders ? 1 : 0;
+    s->viscous = viscosity > 0.0;
+    if (s->viscous) {           // fluid_simulator.py:327-336, in double then narrowed
+        const double centre = 1.0 / viscosity;
+        s->alpha = (float)centre;
+        s->rbeta = (float)(1.0 / (4.0 + centre));
+    }
+    return 0;
+}
+
+int natrix_set_option(natrix_sim* s, int option, int value) {
+    NEED(s, "null simulator");
+    switch (option) {
+    case NATRIX_OPT_PIPELINE:
+        NEED(value == 0 || value == 1, "pipeline must be 0 or 1");
+        if (int rc = select_device(s)) return rc;
+        if (int rc = flush_splats(s)) return rc;
+        s->pipeline = value; return 0;
+    case NATRIX_OPT_JACOBI_DEPTH:
+        NEED(value >= 1 && value <= JACOBI_TB_MAX_DEPTH, "jacobi depth out of range");
+        s->jacobi_depth = value; return 0;
+    case NATRIX_OPT_TIMING: s->timing = value ? 1 : 0; return 0;
+    case NATRIX_OPT_GRAPH: s->graph = value ? 1 : 0; return 0;
+    case NATRIX_OPT_PACKED: s->packed = value ? 1 : 0; return 0;
+    default: return fail(NATRIX_ERR_ARG, "unknown option id");
+    }
+}
+
+int natrix_get_option(natrix_sim* s, int option, int* value) {
+    NEED(s && value, "null argument");
+    switch (option) {
+    case NATRIX_OPT_PIPELINE: *value = s->pipeline; return 0;
+    case NATRIX_OPT_JACOBI_DEPTH: *value = s->jacobi_depth; return 0;
+    case NATRIX_OPT_TIMING: *value = s->timing; return 0;
+    case NATRIX_OPT_GRAPH: *value = s->graph; return 0;
+    case NATRIX_OPT_PACKED: *value = s->packed; return 0;
+    default: return fail(NATRIX_ERR_ARG, "unknown option id");
+    }
+}
+
+int natrix_add_velocity(natrix_sim* s, float px, float py, float vx, float vy, float radius) {
+    NEED(s, "null simulator");
+    // splat_pos = _Position * _Size (shader.AddVelocity.comp:27), float32 products
+    SplatV sp{px * (float)s->g.w, py * (float)s->g.hg, vx, vy, radius};
+    s->pending.push_back(sp);
+    if (s->pipeline == 0) {
+        if (int rc = select_device(s)) return rc;
+        return flush_splats(s);          // one dispatch per call, like the reference
+    }
+    return 0;
+}
+
+int natrix_add_circle_obstacle(natrix_sim* s, float px, float py, float radius, int is_static) {
+    NEED(s, "null simulator");
+    (void)is_static;                      // both shader branches write (1,0): SURVEY Q17
+    if (int rc = select_device(s)) return rc;
+    const Geom& g = s->g;
+    s->launches += launch_add_circle(s->obs, g, s->ext_lo(g.halo), s->ext_hi(g.halo), px * (float)g.w,
+                                     py * (float)g.hg, radius, s->pipeline != 0, s->st);
+    s->obs_dirty = true;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int natrix_add_triangle_obstacle(natrix_sim* s, float p1x, float p1y, float p2x, float p2y, float p3x,
+                                 float p3y, int is_static) {
+    NEED(s, "null simulator");
+    if (int rc = select_device(s)) return rc;
+    const Geom& g = s->g;
+    s->launches += launch_add_triangle(s->obs, g, s->ext_lo(g.halo), s->ext_hi(g.halo), p1x, p1y, p2x, p2y,
+                                       p3x, p3y, is_static, s->st);
+    s->obs_dirty = true;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int natrix_step_phase(natrix_sim* s, int phase, float dt, int sweeps) {
+    NEED(s, "null simulator");
+    if (int rc = select_device(s)) return rc;
+    switch (phase) {
+    case 0: return phase_advect(s, dt);
+    case 1: return phase_forces(s, dt);
+    case 2:
+        NEED(sweeps > 0, "sweeps must be positive");
+        stamp(s, ST_JACOBI);
+        return phase_jacobi(s, sweeps);
+    case 3: {
+        if (int rc = phase_project(s)) return rc;
+        return check_range_flag(s);
+    }
+    default: return fail(NATRIX_ERR_ARG, "phase must be 0..3");
+    }
+}
+
+int natrix_halo_rows_needed(natrix_sim* s, int phase, float dt) {
+    if (!s) return fail(NATRIX_ERR_ARG, "null simulator");
+    switch (phase) {
+    case 0: {
+        // |v| <= 1 after add_velocity / advect clamps; the projection can exceed it slightly, so
+        // the reach is padded and the kernel reports (NATRIX_ERR_RANGE) if it was not enough.
+        const double reach = std::ceil(1.25 * (double)dt * (double)s->speed) + 1.0;
+        return (int)reach + 4;
+    }
+    case 1: return 0;                 // phase 0 already produced rows ext(4)
+    case 2: return s->jacobi_depth;
+    case 3: return 1;
+    default: return fail(NATRIX_ERR_ARG, "phase must be 0..3");
+    }
+}
+
+int natrix_halo_region(natrix_sim* s, int field, int side, int rows, void** send_ptr, void** recv_ptr,
+                       size_t* bytes) {
+    NEED(s && send_ptr && recv_ptr && bytes, "null argument");
+    NEED(side == 0 || side == 1, "side must be 0 or 1");
+    NEED(rows >= 0 && rows <= s->g.halo && rows <= s->g.hl, "rows exceed the slab's halo");
+    if (int rc = select_device(s)) return rc;
+    if (field == NATRIX_VELOCITY)
+        if (int rc = flush_splats(s)) return rc;
+    void* row0 = nullptr;
+    size_t elem = 0;
+    if (int rc = field_info(s, field, &row0, &elem)) return rc;
+    const size_t row_bytes = (size_t)s->g.w * elem;
+    char* base = (char*)row0;
+    if (side == 0) {
+        *send_ptr = base;
+        *recv_ptr = base - (ptrdiff_t)rows * (ptrdiff_t)row_bytes;
+    } else {
+        *send_ptr = base + (size_t)(s->g.hl - rows) * row_bytes;
+        *recv_ptr = base + (size_t)s->g.hl * row_bytes;
+    }
+    *bytes = (size_t)rows * row_bytes;
+    return 0;
+}
+
+int natrix_step(natrix_sim* s, float dt) {
+    NEED(s, "null simulator");
+    if (s->g.hl != s->g.hg)
+        return fail(NATRIX_ERR_STATE, "natrix_step needs the full grid; slabs use natrix_step_phase");
+    if (int rc = select_device(s)) return rc;
+    if (int rc = phase_advect(s, dt)) return rc;
+    if (int rc = phase_forces(s, dt)) return rc;
+    stamp(s, ST_JACOBI);
+    if (int rc = phase_jacobi(s, s->iterations)) return rc;
+    if (int rc = phase_project(s)) return rc;
+    return 0;
+}
+
+int natrix_field_ptr(natrix_sim* s, int field, void** dev_ptr, size_t* bytes) {
+    NEED(s && dev_ptr, "null argument");
+    if (int rc = select_device(s)) return rc;
+    if (field == NATRIX_VELOCITY)
+        if (int rc = flush_splats(s)) return rc;
+    size_t elem = 0;
+    if (int rc = field_info(s, field, dev_ptr, &elem)) return rc;
+    if (bytes) *bytes = (size_t)s->g.w * s->g.hl * elem;
+    return 0;
+}
+
+int natrix_copy_out(natrix_sim* s, int field, void* host, size_t bytes) {
+    NEED(s && host, "null argument");
+    if (int rc = select_device(s)) return rc;
+    if (field == NATRIX_VELOCITY)
+        if (int rc = flush_splats(s)) return rc;
+    void* src = nullptr;
+    size_t elem = 0;
+    if (int rc = field_info(s, field, &src, &elem)) return rc;
+    const size_t n = (size_t)s->g.w * s->g.hl;
+    if (field == NATRIX_OBSTACLES) {
+        NEED(bytes == n * sizeof(float2), "OBSTACLES copy_out expects width*height*8 bytes");
+        if (!s->d_tmp2) CU(cudaMalloc((void**)&s->d_tmp2, n * sizeof(float2)));
+        s->launches += launch_obs_expand(s->obs, s->d_tmp2, n, s->st);
+        src = s->d_tmp2;
+        elem = sizeof(float2);
+    }
+    NEED(bytes == n * elem, "copy_out size does not match the field");
+    CU(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+
+int natrix_copy_in(natrix_sim* s, int field, const void* host, size_t bytes) {
+    NEED(s && host, "null argument");
+    if (int rc = select_device(s)) return rc;
+    if (field == NATRIX_VELOCITY)
+        if (int rc = flush_splats(s)) return rc;
+    void* dst = nullptr;
+    size_t elem = 0;
+    if (int rc = field_info(s, field, &dst, &elem)) return rc;
+    const size_t n = (size_t)s->g.w * s->g.hl;
+    if (field == NATRIX_OBSTACLES) {
+        NEED(bytes == n * sizeof(float2), "OBSTACLES copy_in expects width*height*8 bytes");
+        if (!s->d_tmp2) CU(cudaMalloc((void**)&s->d_tmp2, n * sizeof(float2)));
+        CU(cudaMemcpyAsync(s->d_tmp2, host, bytes, cudaMemcpyHostToDevice, s->st));
+        s->launches += launch_obs_pack(s->d_tmp2, s->obs, n, s->st);
+        s->obs_dirty = true;
+        CU(cudaStreamSynchronize(s->st));
+        return 0;
+    }
+    NEED(bytes == n * elem, "copy_in size does not match the field");
+    CU(cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    if (field == NATRIX_PRESSURE) s->p_is_zero = false;
+    return 0;
+}
+
+int natrix_field_stats(natrix_sim* s, int field, double* out4) {
+    NEED(s && out4, "null argument");
+    NEED(field >= NATRIX_VELOCITY && field <= NATRIX_VORTICITY, "stats are defined for float fields");
+    if (int rc = select_device(s)) return rc;
+    if (field == NATRIX_VELOCITY)
+        if (int rc = flush_splats(s)) return rc;
+    void* src = nullptr;
+    size_t elem = 0;
+    if (int rc = field_info(s, field, &src, &elem)) return rc;
+    const size_t nfl = (size_t)s->g.w * s->g.hl * (elem / sizeof(float));
+    s->launches += launch_stats((const float*)src, nfl, s->d_scratch, s->d_out4, s->st);
+    CU(cudaMemcpyAsync(s->h_out4, s->d_out4, 4 * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    memcpy(out4, s->h_out4, 4 * sizeof(double));
+    return 0;
+}
+
+// ---- dye ---------------------------------------------------------------------------------------
+int natrix_dye_create(natrix_sim* s, int width, int height, natrix_dye** out) {
+    NEED(s && out, "null argument");
+    *out = nullptr;
+    NEED(width > 0 && height > 0, "width and height must be positive");
+    NEED(s->g.hl == s->g.hg, "dye fields need the full velocity grid on this device");
+    if (int rc = select_device(s)) return rc;
+    natrix_dye* d = new natrix_dye();
+    d->sim = s; d->w = width; d->h = height;
+    const size_t bytes = (size_t)width * height * sizeof(float);
+    for (int i = 0; i < 2; ++i) {
+        cudaError_t e = cudaMalloc((void**)&d->d[i], bytes);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d->d[i], 0, bytes, s->st);
+        if (e != cudaSuccess) {
+            cudaFree(d->d[0]); cudaFree(d->d[1]); delete d;
+            return fail(NATRIX_ERR_CUDA, std::string("natrix_dye_create: ") + cudaGetErrorString(e));
+        }
+    }
+    s->dyes.push_back(d);
+    *out = d;
+    return 0;
+}
+
+int natrix_dye_destroy(natrix_dye* d) {
+    if (!d) return 0;
+    if (d->sim) {
+        cudaSetDevice(d->sim->device);
+        cudaStreamSynchronize(d->sim->st);
+        auto& v = d->sim->dyes;
+        for (size_t i = 0; i < v.size(); ++i) if (v[i] == d) { v.erase(v.begin() + i); break; }
+    }
+    cudaFree(d->d[0]); cudaFree(d->d[1]);
+    delete d;
+    return 0;
+}
+
+#define DYE_LIVE(d) NEED((d) && (d)->sim, "dye handle is null or its simulator was destroyed")
+
+int natrix_dye_add(natrix_dye* d, float px, float py, float radius, float strength) {
+    DYE_LIVE(d);
+    SplatD sp{px * (float)d->w, py * (float)d->h, radius, strength};
+    d->pending.push_back(sp);
+    if (d->sim->pipeline == 0) {
+        if (int rc = select_device(d->sim)) return rc;
+        return flush_dye(d);
+    }
+    return 0;
+}
+
+int natrix_dye_step(natrix_dye* d, float dt, float speed, float dissipation) {
+    DYE_LIVE(d);
+    natrix_sim* s = d->sim;
+    if (int rc = select_device(s)) return rc;
+    if (int rc = flush_splats(s)) return rc;     // the advect reads the CURRENT velocity
+    if (int rc = flush_dye(d)) return rc;
+    s->launches += launch_dye_advect(d->d[d->rd], d->d[1 - d->rd], d->w, d->h, s->vel[s->vr], s->obs, s->g.w,
+                                     s->g.hg, dt, speed, dissipation, s->st);
+    d->rd = 1 - d->rd;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int natrix_dye_field_ptr(natrix_dye* d, void** dev_ptr, size_t* bytes) {
+    DYE_LIVE(d);
+    NEED(dev_ptr, "null argument");
+    if (int rc = select_device(d->sim)) return rc;
+    if (int rc = flush_dye(d)) return rc;
+    *dev_ptr = d->d[d->rd];
+    if (bytes) *bytes = (size_t)d->w * d->h * sizeof(float);
+    return 0;
+}
+
+int natrix_dye_copy_out(natrix_dye* d, void* host, size_t bytes) {
+    DYE_LIVE(d);
+    NEED(host && bytes == (size_t)d->w * d->h * sizeof(float), "dye copy_out size mismatch");
+    if (int rc = select_device(d->sim)) return rc;
+    if (int rc = flush_dye(d)) return rc;
+    CU(cudaMemcpyAsync(host, d->d[d->rd], bytes, cudaMemcpyDeviceToHost, d->sim->st));
+    CU(cudaStreamSynchronize(d->sim->st));
+    return 0;
+}
+
+int natrix_dye_copy_in(natrix_dye* d, const void* host, size_t bytes) {
+    DYE_LIVE(d);
+    NEED(host && bytes == (size_t)d->w * d->h * sizeof(float), "dye copy_in size mismatch");
+    if (int rc = select_device(d->sim)) return rc;
+    if (int rc = flush_dye(d)) return rc;
+    CU(cudaMemcpyAsync(d->d[d->rd], host, bytes, cudaMemcpyHostToDevice, d->sim->st));
+    CU(cudaStreamSynchronize(d->sim->st));
+    return 0;
+}
+
+int natrix_dye_stats(natrix_dye* d, double* out4) {
+    DYE_LIVE(d);
+    NEED(out4, "null argument");
+    natrix_sim* s = d->sim;
+    if (int rc = select_device(s)) return rc;
+    if (int rc = flush_dye(d)) return rc;
+    s->launches += launch_stats(d->d[d->rd], (size_t)d->w * d->h, s->d_scratch, s->d_out4, s->st);
+    CU(cudaMemcpyAsync(s->h_out4, s->d_out4, 4 * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    memcpy(out4, s->h_out4, 4 * sizeof(double));
+    return 0;
+}
+
+// ---- sync / introspection ------------------------------------------------------------------------
+int natrix_sync(natrix_sim* s) {
+    NEED(s, "null simulator");
+    if (int rc = select_device(s)) return rc;
+    if (int rc = flush_splats(s)) return rc;
+    for (natrix_dye* d : s->dyes)
+        if (int rc = flush_dye(d)) return rc;
+    CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+
+int natrix_stream(natrix_sim* s, void** stream) {
+    NEED(s && stream, "null argument");
+    *stream = (void*)s->st;
+    return 0;
+}
+
+int natrix_get_timings(natrix_sim* s, float* ms, int n) {
+    NEED(s && ms, "null argument");
+    NEED(s->timing, "enable NATRIX_OPT_TIMING before the step");
+    if (int rc = select_device(s)) return rc;
+    CU(cudaStreamSynchronize(s->st));
+    for (int i = 0; i < ST_COUNT; ++i) {
+        float t = 0.0f;
+        CU(cudaEventElapsedTime(&t, s->ev[i], s->ev[i + 1]));
+        s->stage_ms[i] = t;
+    }
+    for (int i = 0; i < n; ++i) ms[i] = i < ST_COUNT ? s->stage_ms[i] : 0.0f;
+    return 0;
+}
+
+int natrix_launch_count(natrix_sim* s, unsigned long long* kernels) {
+    NEED(s && kernels, "null argument");
+    *kernels = s->launches;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,392 @@
+// jacobi_tb.cu - temporally blocked pressure-Jacobi sweeps for sm_100a.
+//
+// ref: shader.Poisson.comp:24-37 applied `depth` times (fluid_simulator.py:251-255).  One launch
+// advances the pressure field by T = depth sweeps while reading p, div and the blocked-neighbour
+// mask once and writing p once: 13 B/cell per T sweeps instead of 20 B/cell per sweep.
+//
+// Decomposition.  The output rows are cut into tiles of SW = 128 columns x CH rows; ONE WARP owns
+// one tile and needs no other warp: a lane holds 4 adjacent columns (one float4, so its shared-
+// memory reads are bank-conflict free) and keeps, for every time level 0..T-1, the two most
+// recent rows in registers (2*T*4 floats).  The warp marches down its tile
+// one input row at a time; when input row i arrives, level t produces row i-t from the three rows
+// i-t-1, i-t, i-t+1 of level t-1 (left/right neighbours across lanes by warp shuffle), so row i-T
+// of level T leaves the registers T rows behind the load front.  Halo cells (T columns on each
+// side of the strip, T rows above and below the chunk) are recomputed redundantly; they see
+// exactly the same inputs in exactly the same order as in a 1-sweep-per-launch kernel, so the
+// result is bit-identical.
+//
+// Staging.  Input rows come through TMA (cp.async.bulk.tensor.2d, SASS UTMALDG): each warp runs
+// its own ring of 2-row x 128-column boxes for p (8 rows), div (16 rows: a div row is needed again by every
+// level for T more iterations) and the mask (8 rows), completed on 4 warp-private mbarriers and
+// issued 3 groups (6 rows) ahead by lane 0.  Out-of-bounds parts of a box (strip halos beyond the
+// grid, rows beyond the slab) are zero-filled by TMA; those values only ever feed cells whose
+// results are discarded, because every in-domain cell next to the edge carries the "blocked"
+// bit for that direction and substitutes its own pressure (the shader's clamp-to-edge rule).
+//
+// Obstacles.  Warps whose rows in flight have an all-zero mask run a select-free body
+// (5 FP instructions per cell-sweep); otherwise a body with 4 selects per cell.
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "jacobi_tb.h"
+#include "kernels.h"
+
+namespace natrix {
+
+namespace {
+
+constexpr int SW = 128;                 // strip width: columns per warp tile, 4 per lane
+constexpr int WARPS = 8;                // warps (= tiles) per block; 2 blocks per SM
+constexpr int P_ROWS = 8, M_ROWS = 8, D_ROWS = 16;
+constexpr int GROUP = 2;                // rows per TMA box
+constexpr int PD = 3;                   // groups issued ahead of consumption
+constexpr int NBAR = 4;                 // mbarriers per warp (PD in flight + 1 being consumed)
+
+struct __align__(128) WarpSmem {
+    float p[P_ROWS][SW];
+    float d[D_ROWS][SW];
+    uint8_t m[M_ROWS][SW];
+    unsigned long long bar[NBAR];
+    unsigned char pad[128 - NBAR * 8];
+};
+static_assert(sizeof(WarpSmem) % 128 == 0, "per-warp shared memory must keep 128 B alignment");
+constexpr size_t SMEM_BYTES = WARPS * sizeof(WarpSmem);
+
+struct TBParams {
+    float* pout;      // local row 0 of the output field
+    int w;            // grid width
+    int halo;         // tensor-map row = local row + halo
+    int r0, r1;       // output rows [r0, r1)
+    int ch;           // rows per chunk
+    int nstrips;      // strips per chunk
+    int ntiles;       // nstrips * nchunks
+    int hx;           // halo columns on each side of a strip (>= T, multiple of 4)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// shared-memory byte addresses of this lane's 16-byte column group in the three rings
+struct LaneAddr { uint32_t p, d, m; };
+
+// One input row: advance every time level by one row.  a[t][.] holds the two newest rows of
+// level t (slot PAR = older, PAR^1 = newer); afterwards slot PAR holds the newest.
+// Column j of a lane is strip column 4*lane + j.
+template <int T, bool PZERO, int PAR, bool SLOW>
+__device__ __forceinline__ void row_step(float (&a)[T][2][4], const uint32_t (&mk)[T], const LaneAddr& sa,
+                                         int i, int lane, float (&out)[4]) {
+    constexpr unsigned FULL = 0xffffffffu;
+    float nw[4];
+    if (PZERO) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) nw[c] = 0.0f;
+    } else {
+        const float4 v = lds128(sa.p + (uint32_t)(i & (P_ROWS - 1)) * (SW * 4));
+        nw[0] = v.x; nw[1] = v.y; nw[2] = v.z; nw[3] = v.w;
+    }
+    const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
+#pragma unroll
+    for (int t = 1; t <= T; ++t) {
+        float(&old)[4] = a[t - 1][PAR];
+        float(&mid)[4] = a[t - 1][PAR ^ 1];
+        const float4 dv = lds128(sa.d + (uint32_t)((i - t) & (D_ROWS - 1)) * (SW * 4));
+        const float d[4] = {dv.x, dv.y, dv.z, dv.w};
+        // left / right neighbours across lanes (lanes 0 and 31 receive wrapped garbage for the
+        // strip's outermost columns, which lie in the discarded halo)
+        const float sl = __shfl_sync(FULL, mid[3], lane_l);
+        const float sr = __shfl_sync(FULL, mid[0], lane_r);
+        float res[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float C = mid[j];
+            float x1 = j > 0 ? mid[j - 1] : sl;
+            float x2 = j < 3 ? mid[j + 1] : sr;
+            float y1 = old[j];       // row - 1 ("B")
+            float y2 = nw[j];        // row + 1 ("T")
+            if (SLOW) {
+                const uint32_t bits = mk[t - 1] >> (8 * j);
+                x1 = (bits & NB_L) ? C : x1;
+                x2 = (bits & NB_R) ? C : x2;
+                y1 = (bits & NB_B) ? C : y1;
+                y2 = (bits & NB_T) ? C : y2;
+            }
+            res[j] = (x1 + x2 + y1 + y2 - d[j]) * 0.25f;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { old[c] = nw[c]; nw[c] = res[c]; }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[c] = nw[c];
+}
+
+template <int T, bool PZERO>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_d,
+            const __grid_constant__ CUtensorMap map_m, const TBParams prm) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * WARPS + warp;
+    if (tile >= prm.ntiles) return;                 // warps are independent: no block barrier below
+    WarpSmem& S = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
+
+    const int chunk = tile / prm.nstrips, strip = tile - chunk * prm.nstrips;
+    const int x0 = strip * (SW - 2 * prm.hx) - prm.hx;      // first strip column (may be < 0)
+    const int out_lo = prm.r0 + chunk * prm.ch;
+    const int out_hi = min(out_lo + prm.ch, prm.r1);
+    const int y_first = out_lo - T;                          // first input row (local)
+    const int nrows = (out_hi - out_lo) + 2 * T;
+    const int ngroups = (nrows + GROUP - 1) / GROUP;
+
+    const uint32_t bar0 = smem_u32(&S.bar[0]);
+    const uint32_t p_addr = smem_u32(&S.p[0][0]), d_addr = smem_u32(&S.d[0][0]), m_addr = smem_u32(&S.m[0][0]);
+    if ((p_addr & 127u) != 0u) __trap();             // TMA destinations must be 128 B aligned
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < NBAR; ++b) mbar_init(bar0 + 8 * b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
+    auto issue = [&](int g) {   // lane 0 only
+        const uint32_t bar = bar0 + 8 * (g & (NBAR - 1));
+        const int row = y_first + GROUP * g + prm.halo;
+        constexpr uint32_t BYTES = GROUP * SW * (PZERO ? 5u : 9u);
+        mbar_expect_tx(bar, BYTES);
+        if (!PZERO) tma_load_2d(p_addr + ((GROUP * g) & (P_ROWS - 1)) * (SW * 4), &map_p, x0, row, bar);
+        tma_load_2d(d_addr + ((GROUP * g) & (D_ROWS - 1)) * (SW * 4), &map_d, x0, row, bar);
+        tma_load_2d(m_addr + ((GROUP * g) & (M_ROWS - 1)) * SW, &map_m, x0, row, bar);
+    };
+    if (lane == 0) {
+        for (int g = 0; g < PD && g < ngroups; ++g) issue(g);
+    }
+
+    float a[T][2][4];
+    uint32_t mk[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        mk[t] = 0u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { a[t][0][c] = 0.0f; a[t][1][c] = 0.0f; }
+    }
+    uint32_t busy = 0u;                               // bit t-1: row i-t has a non-zero mask somewhere in the warp
+    constexpr uint32_t BUSY_MASK = (1u << T) - 1u;
+
+    const LaneAddr sa{p_addr + 16u * lane, d_addr + 16u * lane, m_addr + 4u * lane};
+    const int xa = x0 + 4 * lane;                     // this lane's first grid column
+    const bool st_ok = 4 * lane >= prm.hx && 4 * lane < SW - prm.hx && xa < prm.w;
+    float* const out_col = prm.pout + xa;
+
+    auto finish_row = [&](int i, const float (&res)[4]) {
+        // shift the mask history and take in the mask bytes of input row i
+        const uint32_t mnew = lds32(sa.m + (uint32_t)(i & (M_ROWS - 1)) * SW) & 0x0f0f0f0fu;
+#pragma unroll
+        for (int t = T - 1; t > 0; --t) mk[t] = mk[t - 1];
+        mk[0] = mnew;
+        busy = ((busy << 1) | (__any_sync(0xffffffffu, mnew != 0u) ? 1u : 0u)) & BUSY_MASK;
+        const int ly = y_first + i - T;               // row of level T that just completed
+        if (st_ok && ly >= out_lo && ly < out_hi)
+            stg_stream(reinterpret_cast<float4*>(out_col + (ptrdiff_t)ly * prm.w),
+                       make_float4(res[0], res[1], res[2], res[3]));
+    };
+
+    for (int g = 0; g < ngroups; ++g) {
+        const uint32_t bar = bar0 + 8 * (g & (NBAR - 1));
+        const uint32_t parity = (g / NBAR) & 1;
+        while (!mbar_try_wait(bar, parity)) {}
+        float res[4];
+        const int i0 = GROUP * g;
+        if (busy) row_step<T, PZERO, 0, true>(a, mk, sa, i0, lane, res);
+        else row_step<T, PZERO, 0, false>(a, mk, sa, i0, lane, res);
+        finish_row(i0, res);
+        if (busy) row_step<T, PZERO, 1, true>(a, mk, sa, i0 + 1, lane, res);
+        else row_step<T, PZERO, 1, false>(a, mk, sa, i0 + 1, lane, res);
+        finish_row(i0 + 1, res);
+        __syncwarp();
+        if (lane == 0 && g + PD < ngroups) issue(g + PD);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct MapEntry {
+    const void* base;
+    int w;
+    size_t rows;
+    int elem;
+    CUtensorMap map;
+};
+
+using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TBParams);
+
+template <int T>
+KernelFn pick(bool pzero) { return pzero ? k_jacobi_tb<T, true> : k_jacobi_tb<T, false>; }
+
+KernelFn kernel_for(int depth, bool pzero) {
+    switch (depth) {
+    case 1: return pick<1>(pzero);
+    case 2: return pick<2>(pzero);
+    case 3: return pick<3>(pzero);
+    case 4: return pick<4>(pzero);
+    case 5: return pick<5>(pzero);
+    case 6: return pick<6>(pzero);
+    case 7: return pick<7>(pzero);
+    case 8: return pick<8>(pzero);
+    default: return nullptr;
+    }
+}
+
+}  // namespace
+
+struct JacobiTB {
+    EncodeTiledFn encode = nullptr;
+    std::string err;
+    int sm_count = 148;
+    int chunk_override = 0;
+    std::vector<MapEntry> maps;
+    bool attr_set[JACOBI_TB_MAX_DEPTH + 1][2] = {};
+
+    const CUtensorMap* map_for(const void* base, int w, size_t rows, int elem) {
+        for (const MapEntry& e : maps)
+            if (e.base == base && e.w == w && e.rows == rows && e.elem == elem) return &e.map;
+        if (!encode) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            cudaError_t ce = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+            if (ce != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+                err = "cuTensorMapEncodeTiled is not available from the CUDA driver";
+                return nullptr;
+            }
+            encode = (EncodeTiledFn)fn;
+        }
+        MapEntry e{base, w, rows, elem, {}};
+        const cuuint64_t gdim[2] = {(cuuint64_t)w, (cuuint64_t)rows};
+        const cuuint64_t gstride[1] = {(cuuint64_t)w * (cuuint64_t)elem};
+        const cuuint32_t box[2] = {(cuuint32_t)SW, (cuuint32_t)GROUP};
+        const cuuint32_t estride[2] = {1, 1};
+        CUresult r = encode(&e.map, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                            const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+            return nullptr;
+        }
+        if (maps.size() >= 64) maps.erase(maps.begin());
+        maps.push_back(e);
+        return &maps.back().map;
+    }
+};
+
+JacobiTB* jacobi_tb_create() {
+    JacobiTB* tb = new JacobiTB();
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) tb->sm_count = n;
+    }
+    if (const char* e = getenv("NATRIX_TB_CHUNK")) tb->chunk_override = atoi(e);
+    return tb;
+}
+
+void jacobi_tb_destroy(JacobiTB* tb) { delete tb; }
+const char* jacobi_tb_error(JacobiTB* tb) { return tb ? tb->err.c_str() : "null JacobiTB"; }
+
+bool jacobi_tb_supported(const Geom& g) {
+    // TMA needs 16-byte row pitches for the float fields and the byte mask
+    return g.w % 16 == 0 && g.w >= SW;
+}
+
+int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div, const uint8_t* nbmask, float* pout, Geom g,
+                     int depth, int r0, int r1, bool p_is_zero, int packed, cudaStream_t st) {
+    (void)packed;
+    if (!tb) return -1;
+    if (depth < 1 || depth > JACOBI_TB_MAX_DEPTH) { tb->err = "depth out of range"; return -1; }
+    if (!jacobi_tb_supported(g)) { tb->err = "grid width must be a multiple of 16 and >= 256"; return -1; }
+    if (r1 <= r0) return 0;
+    const size_t rows_alloc = (size_t)g.hl + 2 * (size_t)g.halo;
+    const ptrdiff_t off = (ptrdiff_t)g.halo * g.w;
+    const CUtensorMap* mp = tb->map_for(pin - off, g.w, rows_alloc, 4);
+    if (!mp) return -1;
+    const CUtensorMap map_p = *mp;            // copy: the cache vector may reallocate
+    const CUtensorMap* md = tb->map_for(div - off, g.w, rows_alloc, 4);
+    if (!md) return -1;
+    const CUtensorMap map_d = *md;
+    const CUtensorMap* mm = tb->map_for(nbmask - off, g.w, rows_alloc, 1);
+    if (!mm) return -1;
+    const CUtensorMap map_m = *mm;
+
+    TBParams prm;
+    prm.pout = pout;
+    prm.w = g.w;
+    prm.halo = g.halo;
+    prm.r0 = r0;
+    prm.r1 = r1;
+    prm.hx = depth <= 4 ? 4 : 8;
+    prm.nstrips = (g.w + (SW - 2 * prm.hx) - 1) / (SW - 2 * prm.hx);
+    const int rows = r1 - r0;
+    int ch = tb->chunk_override;
+    if (ch <= 0) {
+        // about one tile per resident warp (WARPS per SM), but never chunks so short that the
+        // 2*depth warm-up rows dominate
+        int nchunks = (tb->sm_count * WARPS) / prm.nstrips;
+        if (nchunks < 1) nchunks = 1;
+        ch = (rows + nchunks - 1) / nchunks;
+        if (ch < 4 * depth) ch = 4 * depth;
+    }
+    ch = (ch + 1) & ~1;
+    prm.ch = ch;
+    const int nchunks = (rows + ch - 1) / ch;
+    prm.ntiles = prm.nstrips * nchunks;
+    const int blocks = (prm.ntiles + WARPS - 1) / WARPS;
+
+    KernelFn fn = kernel_for(depth, p_is_zero);
+    if (!tb->attr_set[depth][p_is_zero ? 1 : 0]) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) { tb->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -1; }
+        tb->attr_set[depth][p_is_zero ? 1 : 0] = true;
+    }
+    fn<<<blocks, WARPS * 32, SMEM_BYTES, st>>>(map_p, map_d, map_m, prm);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { tb->err = std::string("k_jacobi_tb launch: ") + cudaGetErrorString(e); return -1; }
+    return 1;
+}
+
+}  // namespace natrix

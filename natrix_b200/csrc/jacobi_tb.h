@@ -1,0 +1,26 @@
+// jacobi_tb.h - temporally blocked pressure-Jacobi solver (the hot loop).
+#pragma once
+#include "common.cuh"
+
+namespace natrix {
+
+constexpr int JACOBI_TB_MAX_DEPTH = 8;
+
+struct JacobiTB;   // caches TMA descriptors and launch geometry
+
+JacobiTB* jacobi_tb_create();
+void jacobi_tb_destroy(JacobiTB* tb);
+const char* jacobi_tb_error(JacobiTB* tb);
+// The TMA path needs 16-byte row pitches (width % 16 == 0) and width >= 256; other grids use
+// the 1-sweep mask kernel (launch_poisson_mask).
+bool jacobi_tb_supported(const Geom& g);
+
+// Runs `depth` (1..JACOBI_TB_MAX_DEPTH) Jacobi sweeps pin -> pout for local rows [r0, r1).
+// pin / div / nbmask must be valid on rows [r0-depth, r1+depth) clipped to the global domain.
+// p_is_zero: pin is known to be all zero (first block of a step), so it is not read.
+// Returns the number of kernels launched, or -1 on error (see jacobi_tb_error).
+int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div, const uint8_t* nbmask,
+                     float* pout, Geom g, int depth, int r0, int r1, bool p_is_zero, int packed,
+                     cudaStream_t st);
+
+}  // namespace natrix

@@ -1,0 +1,55 @@
+// kernels.h - host-callable launchers of every CUDA kernel in libnatrix_b200.
+// All pointers address LOCAL row 0 of a slab (halo rows live at negative / >= hl indices).
+// Row ranges [r0, r1) are local rows.  Every launcher enqueues on `st` and returns the
+// number of kernels it launched (for natrix_launch_count).
+#pragma once
+#include "common.cuh"
+
+namespace natrix {
+
+struct SplatV { float sx, sy, vx, vy, r; };       // add_velocity: splat_pos = pos * size
+struct SplatD { float sx, sy, r, value; };        // add_particles
+constexpr int MAX_SPLATS = 32;                    // per batched launch
+struct SplatVBatch { int n; SplatV s[MAX_SPLATS]; };
+struct SplatDBatch { int n; SplatD s[MAX_SPLATS]; };
+
+// ---- reference-order pipeline: one kernel per reference shader (stages_ref.cu) -------------
+int launch_init_boundaries(float2* vel, Geom g, int r0, int r1, cudaStream_t st);
+int launch_advect(const float2* vin, const uint8_t* obs, float2* vout, Geom g, int r0, int r1,
+                  float dt, float speed, float diss, bool fold_borders, int* err, cudaStream_t st);
+int launch_vorticity(const float2* vel, float* vort, Geom g, int r0, int r1, cudaStream_t st);
+int launch_confinement(const float2* vin, const float* vort, float2* vout, Geom g, int r0, int r1,
+                       float dt, float scale, cudaStream_t st);
+int launch_viscosity(const float2* vin, float2* vout, Geom g, int r0, int r1, float alpha,
+                     float rbeta, cudaStream_t st);
+int launch_divergence(const float2* vel, const uint8_t* obs, float* div, uint8_t* nbmask, Geom g,
+                      int r0, int r1, cudaStream_t st);
+int launch_poisson_ref(const float* pin, const float* div, const uint8_t* obs, float* pout, Geom g,
+                       int r0, int r1, cudaStream_t st);
+int launch_gradient_ref(const float2* vin, const float* p, const uint8_t* obs, float2* vout, Geom g,
+                        int r0, int r1, cudaStream_t st);
+int launch_add_velocity(const float2* vin, float2* vout, Geom g, int r0, int r1,
+                        const SplatVBatch& b, cudaStream_t st);
+int launch_add_circle(uint8_t* obs, Geom g, int r0, int r1, float sx, float sy, float radius,
+                      bool bbox, cudaStream_t st);
+int launch_add_triangle(uint8_t* obs, Geom g, int r0, int r1, float p1x, float p1y, float p2x,
+                        float p2y, float p3x, float p3y, int is_static, cudaStream_t st);
+int launch_obs_expand(const uint8_t* obs, float2* out, size_t n, cudaStream_t st);
+int launch_obs_pack(const float2* in, uint8_t* obs, size_t n, cudaStream_t st);
+// deterministic sum / sumsq / min / max of n floats; scratch holds >= 4*1024 doubles
+int launch_stats(const float* data, size_t n, double* scratch, double* out4_dev, cudaStream_t st);
+
+// ---- dye (dye.cu) ----------------------------------------------------------------------------
+int launch_dye_add(const float* din, float* dout, int pw, int ph, const SplatDBatch& b,
+                   cudaStream_t st);
+int launch_dye_advect(const float* din, float* dout, int pw, int ph, const float2* vel,
+                      const uint8_t* obs, int vw, int vh, float dt, float speed, float diss,
+                      cudaStream_t st);
+
+// ---- fused pipeline (fused.cu / jacobi_tb.cu) ----------------------------------------------------
+int launch_poisson_mask(const float* pin, const float* div, const uint8_t* nbmask, float* pout,
+                        Geom g, int r0, int r1, cudaStream_t st);
+int launch_gradient_mask(const float2* vin, const float* p, const uint8_t* nbmask, float2* vout,
+                         Geom g, int r0, int r1, cudaStream_t st);
+
+}  // namespace natrix

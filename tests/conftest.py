@@ -1,0 +1,45 @@
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+# Tolerance of BASELINE.json's north_star: rel. tol 1e-5 per field per step, stated as
+# max|a-b| <= 1e-5 * max|b|.  The kernels are written to be bit-identical to
+# the oracle (no FMA, IEEE div/sqrt, same operand order); tests report how many elements differ
+# at all, and most of them assert exact equality on top of the tolerance.
+REL_TOL = 1e-5
+
+
+def field_report(got: np.ndarray, want: np.ndarray):
+    got = np.asarray(got)
+    want = np.asarray(want)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    scale = float(np.max(np.abs(want))) if want.size else 0.0
+    err = float(np.max(np.abs(got.astype(np.float64) - want.astype(np.float64)))) if want.size else 0.0
+    ndiff = int(np.count_nonzero(got != want))
+    return err, scale, ndiff
+
+
+def assert_fields_close(got: dict, want: dict, what: str = "", exact: bool = False):
+    for name, w in want.items():
+        err, scale, ndiff = field_report(got[name], w)
+        assert np.all(np.isfinite(got[name])), f"{what}{name}: non-finite values"
+        assert err <= REL_TOL * max(scale, 1e-30) or err == 0.0, (
+            f"{what}{name}: max|err| {err:.3e} > {REL_TOL} * max|ref| {scale:.3e} ({ndiff} elements differ)")
+        if exact:
+            assert ndiff == 0, f"{what}{name}: {ndiff} elements are not bit-identical (max err {err:.3e})"
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return ROOT / "tests" / "golden"

@@ -1,0 +1,255 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI (ctypes), against
+the oracle on the same seeded inputs.  Bar: BASELINE.json's rel. tol 1e-5 per field per step
+(conftest.REL_TOL); in fact the kernels are written to be bit-identical and most tests assert
+that too.  Full-size cases use size-independent properties (fused pipeline == reference-order
+pipeline bit for bit, temporal blocking depth independence)."""
+import importlib.util
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_fields_close, field_report
+from natrix_b200 import _lib as L
+from natrix_b200 import workloads as W
+from natrix_b200.core.fluid_simulator import FluidSimulator
+from natrix_b200.smooth_particles_area import SmoothParticlesArea
+from oracle.c_oracle import COracleFluidSimulator, COracleSmoothParticlesArea
+from oracle.natrix_oracle import OracleFluidSimulator, OracleSmoothParticlesArea
+
+pytestmark = pytest.mark.gpu
+
+
+def _mg():
+    spec = importlib.util.spec_from_file_location("make_golden", ROOT / "tests" / "golden" / "make_golden.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _sim_cls(pipeline, depth=None):
+    def make(w, h, layout=None, **kw):
+        s = FluidSimulator(w, h, layout, **kw)
+        s.set_option(L.OPT_PIPELINE, pipeline)
+        if depth is not None:
+            s.set_option(L.OPT_JACOBI_DEPTH, depth)
+        return s
+    return make
+
+
+@pytest.mark.parametrize("pipeline", [0, 1])
+def test_small_case_matches_golden_fixture(pipeline, golden_dir):
+    want = np.load(golden_dir / "small_case.npz")
+    got = _mg().small_case(_sim_cls(pipeline), SmoothParticlesArea)
+    assert_fields_close(got, {k: want[k] for k in want.files}, f"pipeline {pipeline}: ", exact=True)
+
+
+@pytest.mark.parametrize("pipeline", [0, 1])
+def test_config1_demo_ten_steps_vs_numpy_oracle(pipeline):
+    """config 1: demo grid 640x360 + dye 1280x720, random initial velocity, 10 frames."""
+    w = W.demo_workload()
+    w.init = "random"
+    gsim, gdye = W.build(w, _sim_cls(pipeline), SmoothParticlesArea)
+    osim, odye = W.build(w, OracleFluidSimulator, OracleSmoothParticlesArea)
+    for k in range(10):
+        W.run_step(w, gsim, gdye, k)
+        W.run_step(w, osim, odye, k)
+        assert_fields_close(W.fields_of(gsim, gdye), W.fields_of(osim, odye), f"step {k}: ", exact=True)
+    gsim.destroy()
+
+
+def test_config1_zero_state_first_frame_dt0():
+    """the demo's first frame has dt = 0 and an all-zero state."""
+    w = W.demo_workload()
+    gsim, gdye = W.build(w, FluidSimulator, SmoothParticlesArea)
+    osim, odye = W.build(w, OracleFluidSimulator, OracleSmoothParticlesArea)
+    for k, dt in enumerate((0.0, W.DT, W.DT)):
+        W.run_step(w, gsim, gdye, k, dt)
+        W.run_step(w, osim, odye, k, dt)
+        assert_fields_close(W.fields_of(gsim, gdye), W.fields_of(osim, odye), f"frame {k}: ", exact=True)
+
+
+@pytest.mark.parametrize("pipeline", [0, 1])
+def test_config2_1024_twenty_steps_vs_c_oracle(pipeline):
+    """config 2: 1024^2, 50 iterations, vorticity confinement, 4 circular obstacles."""
+    w = W.cfg2_workload()
+    gsim, _ = W.build(w, _sim_cls(pipeline), None)
+    osim, _ = W.build(w, COracleFluidSimulator, None)
+    for k in range(20):
+        W.run_step(w, gsim, None, k)
+        W.run_step(w, osim, None, k)
+        if k in (0, 1, 9, 19):
+            assert_fields_close(W.fields_of(gsim), W.fields_of(osim), f"step {k}: ", exact=True)
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_temporal_blocking_is_depth_independent(depth):
+    """T sweeps per launch must equal T launches of one sweep, bit for bit, for every T,
+    including the remainder block (iterations = 19 is not a multiple of any T > 1)."""
+    w, h = 640, 296
+    rng = np.random.default_rng(depth)
+    v0 = (0.6 * rng.uniform(-1, 1, (h, w, 2))).astype(np.float32)
+    out = []
+    for pipeline, d in ((0, None), (1, depth)):
+        s = _sim_cls(pipeline, d)(w, h)
+        s.vorticity, s.viscosity, s.iterations = 0.7, 0.2, 19
+        s.upload("velocity", v0)
+        for _ in range(2):
+            s.add_circle_obstacle((0.3, 0.4), 30.0)
+            s.add_circle_obstacle((0.0, 0.0), 25.0)          # touches the corner
+            s.add_circle_obstacle((0.999, 0.5), 12.0)        # touches the right edge
+            s.add_triangle_obstacle((0.6, 0.2), (0.9, 0.3), (0.7, 0.8), static=True)
+            s.update(W.DT)
+        out.append(W.fields_of(s))
+        s.destroy()
+    assert_fields_close(out[1], out[0], f"depth {depth}: ", exact=True)
+
+
+@pytest.mark.parametrize("w,h", [(97, 61), (256, 40), (272, 33), (1000, 24), (16, 300), (1, 9), (130, 1)])
+def test_ragged_and_degenerate_sizes_vs_oracle(w, h):
+    rng = np.random.default_rng(w + 1000 * h)
+    v0 = rng.uniform(-1.5, 1.5, (h, w, 2)).astype(np.float32)   # |v| > 1: back-traces leave the grid
+    for pipeline in (0, 1):
+        g = _sim_cls(pipeline)(w, h)
+        o = OracleFluidSimulator(w, h)
+        for s in (g, o):
+            s.vorticity, s.viscosity, s.iterations, s.speed = 2.0, 0.3, 11, 300.0
+        g.upload("velocity", v0)
+        o.velocity = v0
+        for k in range(3):
+            for s in (g, o):
+                s.add_circle_obstacle((0.4, 0.6), min(w, h) / 5.0)
+                s.update(W.DT)
+                s.add_velocity((0.5, 0.5), (0.7, -0.4), 4.0)
+            assert_fields_close(W.fields_of(g), W.fields_of(o), f"{w}x{h} p{pipeline} step {k}: ", exact=True)
+        g.destroy()
+
+
+@pytest.mark.parametrize("borders,visc,vort", [(False, 0.0, 0.0), (True, 0.0, 3.0), (False, 2.0, 0.5)])
+def test_parameter_corners_vs_oracle(borders, visc, vort):
+    w, h = 320, 200
+    v0 = W.random_velocity(w, h, seed=11)
+    g, o = FluidSimulator(w, h), OracleFluidSimulator(w, h)
+    for s in (g, o):
+        s.has_borders, s.viscosity, s.vorticity, s.iterations, s.dissipation = borders, visc, vort, 23, 0.97
+    g.upload("velocity", v0)
+    o.velocity = v0
+    for k in range(3):
+        for s in (g, o):
+            s.add_triangle_obstacle((0.2, 0.2), (0.5, 0.25), (0.3, 0.7))
+            s.update(W.DT)
+        assert_fields_close(W.fields_of(g), W.fields_of(o), f"step {k}: ", exact=True)
+
+
+def test_impulses_and_obstacles_vs_oracle():
+    w, h = 300, 180
+    g, o = FluidSimulator(w, h), OracleFluidSimulator(w, h)
+    v0 = (3.0 * W.random_velocity(w, h, seed=2)).astype(np.float32)        # |v| up to 1.5
+    g.upload("velocity", v0)
+    o.velocity = v0
+    for s in (g, o):
+        s.add_circle_obstacle((0.25, 0.5), 20.0)
+        s.add_circle_obstacle((1.2, 0.5), 80.0, static=True)               # centre outside the grid
+        s.add_circle_obstacle((0.5, 0.5), -1.0)                            # negative radius: nothing
+        s.add_triangle_obstacle((0.5, 0.1), (0.9, 0.2), (0.6, 0.9), static=True)
+        s.add_triangle_obstacle((0.1, 0.6), (0.3, 0.7), (0.2, 0.95), static=False)
+        s.add_velocity((0.5, 0.5), (0.4, -0.9), 25.0)
+        s.add_velocity((0.1, 0.9), (-2.0, 2.0), 60.0)
+    assert np.array_equal(g.download("obstacles"), o.obstacles)
+    got = g.download("velocity")
+    assert np.array_equal(got, o.velocity)
+    assert np.all(np.abs(got) <= 1.0)                                       # Q7: every cell clamped
+    g.update(W.DT)
+    o.update(W.DT)
+    assert not g.download("obstacles").any()                                # Q8: cleared by update
+    assert_fields_close(W.fields_of(g), W.fields_of(o), exact=True)
+
+
+def test_simulate_false_gates_every_mutator():
+    g = FluidSimulator(64, 64)
+    v0 = W.random_velocity(64, 64, 1)
+    g.upload("velocity", v0)
+    g.simulate = False
+    g.add_velocity((0.5, 0.5), (1, 1), 10.0)
+    g.add_circle_obstacle((0.5, 0.5), 10.0)
+    g.update(W.DT)
+    assert np.array_equal(g.download("velocity"), v0)
+    assert not g.download("obstacles").any()
+
+
+def test_dye_cross_resolution_vs_oracle():
+    w, h = 200, 120
+    g, o = FluidSimulator(w, h), OracleFluidSimulator(w, h)
+    gd, od = SmoothParticlesArea(333, 250, g), OracleSmoothParticlesArea(333, 250, o)
+    v0 = W.random_velocity(w, h, 4)
+    g.upload("velocity", v0)
+    o.velocity = v0
+    for d in (gd, od):
+        d.dissipation, d.speed = 0.95, 400.0
+        d.add_particles((0.5, 0.5), 60.0, 3.0)
+        d.add_particles((0.2, 0.7), 30.0, 300.0)       # saturates the 255 clamp
+    for k in range(3):
+        for s, d in ((g, gd), (o, od)):
+            s.add_circle_obstacle((0.6, 0.4), 15.0)
+            d.update(W.DT)                              # sees the obstacle (added before update)
+            s.update(W.DT)
+            d.update(W.DT)                              # obstacle map is empty again
+        err, scale, ndiff = field_report(gd.download(), od.particles)
+        assert ndiff == 0, (k, err, scale)
+
+
+def test_zero_copy_views_and_stats():
+    import torch
+
+    g = FluidSimulator(256, 128)
+    v0 = W.random_velocity(256, 128, 9)
+    g.upload("velocity", v0)
+    buf = g.get_velocity_buffer()
+    t = torch.as_tensor(buf, device="cuda:0")
+    g.synchronize()
+    assert t.shape == (128, 256, 2) and t.data_ptr() == buf.data_ptr
+    assert np.array_equal(t.cpu().numpy(), v0)
+    assert np.array_equal(buf.numpy(), v0)
+    s, q, lo, hi = g.stats("velocity")
+    assert np.isclose(s, v0.astype(np.float64).sum(), rtol=1e-12, atol=1e-9)
+    assert np.isclose(q, (v0.astype(np.float64) ** 2).sum(), rtol=1e-12)
+    assert (lo, hi) == (float(v0.min()), float(v0.max()))
+
+
+def test_errors_are_loud():
+    g = FluidSimulator(64, 64)
+    g.destroy()
+    with pytest.raises(L.NatrixError):
+        g.update(W.DT)
+    with pytest.raises(L.NatrixError):
+        FluidSimulator(0, 10)
+    g2 = FluidSimulator(32, 32)
+    import ctypes as C
+    buf = np.zeros(5, np.uint8)
+    rc = g2._lib.natrix_copy_in(g2._handle(), 0, buf.ctypes.data_as(C.c_void_p), 5)
+    assert rc == -1 and b"size" in g2._lib.natrix_last_error()
+    with pytest.raises(ValueError):
+        g2.iterations = 0
+
+
+def test_config3_4096_fused_equals_reference_order_pipeline():
+    """config 3 at BASELINE.json's full size.  The CPU oracle is too slow for 4096^2 x 100
+    sweeps x several steps, so the full-size check is the size-independent property that the
+    fused / temporally blocked pipeline is bit-identical to the one-kernel-per-shader pipeline
+    (which the smaller cases pin to the oracle), plus one oracle-checked step with 12 sweeps."""
+    w = W.cfg3_workload()
+    a, ad = W.build(w, _sim_cls(0), SmoothParticlesArea)
+    b, bd = W.build(w, _sim_cls(1), SmoothParticlesArea)
+    for k in range(2):
+        W.run_step(w, a, ad, k)
+        W.run_step(w, b, bd, k)
+    fa, fb = W.fields_of(a, ad), W.fields_of(b, bd)
+    assert_fields_close(fb, fa, "4096^2 fused vs reference-order: ", exact=True)
+    assert float(np.abs(fa["velocity"]).max()) > 0.1 and float(fa["dye"].max()) > 0.0
+    a.destroy()
+    # one step against the C oracle, 12 sweeps
+    w.iterations = 12
+    o, od = W.build(w, COracleFluidSimulator, COracleSmoothParticlesArea)
+    b2, bd2 = W.build(w, _sim_cls(1), SmoothParticlesArea)
+    W.run_step(w, o, od, 0)
+    W.run_step(w, b2, bd2, 0)
+    assert_fields_close(W.fields_of(b2, bd2), W.fields_of(o, od), "4096^2 vs C oracle: ", exact=True)

@@ -1,0 +1,64 @@
+"""CPU tests of host-side logic that needs no device: property validation (same messages as
+the reference), workload generators, slab partitioning."""
+import numpy as np
+import pytest
+
+from natrix_b200 import workloads as W
+from natrix_b200.core.fluid_simulator import FluidSimulator
+from natrix_b200.smooth_particles_area import SmoothParticlesArea
+
+
+class _NoDevice(FluidSimulator):
+    """Exercises the property setters without creating a device handle."""
+
+    def __init__(self):          # noqa: D401 - deliberately skips the C-ABI call
+        self._speed, self._iterations, self._dissipation = 500.0, 50, 1.0
+        self._vorticity, self._viscosity = 0.0, 0.1
+        self._h, self._dyes = None, []
+
+
+def test_defaults_match_reference():
+    s = _NoDevice()
+    assert (s.speed, s.iterations, s.dissipation, s.vorticity, s.viscosity) == (500.0, 50, 1.0, 0.0, 0.1)
+    assert FluidSimulator.has_borders is True and FluidSimulator.simulate is True
+    assert SmoothParticlesArea.simulate is True
+
+
+@pytest.mark.parametrize("attr,bad,msg", [
+    ("speed", 0, "'Speed' should be greater than zero"),
+    ("iterations", 0, "'Iterations' should be grater than zero"),
+    ("dissipation", -1.0, "'Dissipation' should be grater than zero"),
+    ("vorticity", -0.1, "'Vorticity' should be grater or equal than zero"),
+    ("viscosity", -0.1, "'Viscosity' should be greater or equal than zero"),
+])
+def test_property_validation_messages(attr, bad, msg):
+    s = _NoDevice()
+    with pytest.raises(ValueError) as e:
+        setattr(s, attr, bad)
+    assert str(e.value) == msg
+
+
+def test_zero_vorticity_and_viscosity_are_legal():
+    s = _NoDevice()
+    s.vorticity = 0
+    s.viscosity = 0.0
+    assert s.viscosity == 0.0
+
+
+def test_workloads_are_deterministic_and_match_baseline_configs():
+    w3 = W.cfg3_workload()
+    assert (w3.width, w3.height, w3.iterations, w3.splats_per_step) == (4096, 4096, 100, 8)
+    assert W.orbit_positions(w3, 5) == W.orbit_positions(w3, 5)
+    assert len(W.orbit_positions(w3, 5)) == 8
+    w1 = W.demo_workload()
+    assert (w1.width, w1.height, w1.iterations, w1.viscosity, w1.dye_size) == (640, 360, 50, 0.5, (1280, 720))
+    assert W.cfg2_workload().algorithmic_bytes_per_cell_step() == 132 + 20 * 50
+    w5 = W.cfg5_workload(8)
+    assert (w5.width, w5.height, w5.iterations, len(w5.circles)) == (32768, 32768, 200, 64)
+
+
+def test_smooth_velocity_slab_equals_window_of_full_field():
+    full = W.smooth_velocity(128, 96)
+    part = W.smooth_velocity(128, 96, row0=32, rows=40)
+    assert np.array_equal(full[32:72], part)
+    assert np.max(np.abs(full)) <= 0.5
