@@ -46,10 +46,18 @@ constexpr int GROUP = 2;                // rows per TMA box
 constexpr int PD = 3;                   // groups issued ahead of consumption
 constexpr int NBAR = 4;                 // mbarriers per warp (PD in flight + 1 being consumed)
 
+// The mask is 1 byte per cell, and TMA wants the first byte of a box 16-byte aligned in global
+// memory: the strip origin x0 is only a multiple of 4, so the mask box starts at x0 rounded down
+// to 16 and is MBOX = 144 bytes wide; each 2-row box gets its own 128 B aligned slot.
+constexpr int MBOX = SW + 16;
+constexpr int M_SLOT = 384;             // >= GROUP * MBOX, multiple of 128
+constexpr int M_SLOTS = M_ROWS / GROUP;
+static_assert(GROUP * MBOX <= M_SLOT && M_SLOT % 128 == 0, "mask slot too small");
+
 struct __align__(128) WarpSmem {
     float p[P_ROWS][SW];
     float d[D_ROWS][SW];
-    uint8_t m[M_ROWS][SW];
+    uint8_t m[M_SLOTS][M_SLOT];
     unsigned long long bar[NBAR];
     unsigned char pad[128 - NBAR * 8];
 };
@@ -186,11 +194,11 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
     auto issue = [&](int g) {   // lane 0 only
         const uint32_t bar = bar0 + 8 * (g & (NBAR - 1));
         const int row = y_first + GROUP * g + prm.halo;
-        constexpr uint32_t BYTES = GROUP * SW * (PZERO ? 5u : 9u);
+        constexpr uint32_t BYTES = GROUP * (SW * (PZERO ? 4u : 8u) + MBOX);
         mbar_expect_tx(bar, BYTES);
         if (!PZERO) tma_load_2d(p_addr + ((GROUP * g) & (P_ROWS - 1)) * (SW * 4), &map_p, x0, row, bar);
         tma_load_2d(d_addr + ((GROUP * g) & (D_ROWS - 1)) * (SW * 4), &map_d, x0, row, bar);
-        tma_load_2d(m_addr + ((GROUP * g) & (M_ROWS - 1)) * SW, &map_m, x0, row, bar);
+        tma_load_2d(m_addr + (g & (M_SLOTS - 1)) * M_SLOT, &map_m, x0 & ~15, row, bar);
     };
     if (lane == 0) {
         for (int g = 0; g < PD && g < ngroups; ++g) issue(g);
@@ -207,14 +215,15 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
     uint32_t busy = 0u;                               // bit t-1: row i-t has a non-zero mask somewhere in the warp
     constexpr uint32_t BUSY_MASK = (1u << T) - 1u;
 
-    const LaneAddr sa{p_addr + 16u * lane, d_addr + 16u * lane, m_addr + 4u * lane};
+    const LaneAddr sa{p_addr + 16u * lane, d_addr + 16u * lane, m_addr + (uint32_t)(x0 & 15) + 4u * lane};
     const int xa = x0 + 4 * lane;                     // this lane's first grid column
     const bool st_ok = 4 * lane >= prm.hx && 4 * lane < SW - prm.hx && xa < prm.w;
     float* const out_col = prm.pout + xa;
 
     auto finish_row = [&](int i, const float (&res)[4]) {
         // shift the mask history and take in the mask bytes of input row i
-        const uint32_t mnew = lds32(sa.m + (uint32_t)(i & (M_ROWS - 1)) * SW) & 0x0f0f0f0fu;
+        const uint32_t mnew = lds32(sa.m + (uint32_t)((i / GROUP) & (M_SLOTS - 1)) * M_SLOT +
+                                    (uint32_t)(i % GROUP) * MBOX) & 0x0f0f0f0fu;
 #pragma unroll
         for (int t = T - 1; t > 0; --t) mk[t] = mk[t - 1];
         mk[0] = mnew;
@@ -286,6 +295,7 @@ struct JacobiTB {
     const CUtensorMap* map_for(const void* base, int w, size_t rows, int elem) {
         for (const MapEntry& e : maps)
             if (e.base == base && e.w == w && e.rows == rows && e.elem == elem) return &e.map;
+        const int box_w = elem == 4 ? SW : MBOX;
         if (!encode) {
             void* fn = nullptr;
             cudaDriverEntryPointQueryResult q;
@@ -299,7 +309,7 @@ struct JacobiTB {
         MapEntry e{base, w, rows, elem, {}};
         const cuuint64_t gdim[2] = {(cuuint64_t)w, (cuuint64_t)rows};
         const cuuint64_t gstride[1] = {(cuuint64_t)w * (cuuint64_t)elem};
-        const cuuint32_t box[2] = {(cuuint32_t)SW, (cuuint32_t)GROUP};
+        const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)GROUP};
         const cuuint32_t estride[2] = {1, 1};
         CUresult r = encode(&e.map, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
                             const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -1,0 +1,292 @@
+"""Row-slab multi-GPU driver: one process per GPU, halo exchange with torch.distributed.
+
+The reference is single-device; this is new capability.  The global grid
+``width x height`` is cut into contiguous row slabs, one per rank.  Every stage of the step is a
+local stencil or a bounded gather, so the only data-path communication is a point-to-point
+exchange of halo rows with the two neighbouring ranks (NCCL send/recv over NVLink):
+
+    before advect                 velocity     ceil(1.25 dt speed) + 5 rows
+    after divergence              divergence, blocked-neighbour mask     T rows   (T = Jacobi depth)
+    before every Jacobi block     pressure     T rows   (not the first: p starts at zero)
+    before gradient subtraction   pressure     1 row
+
+Obstacles and impulses are functions of global cell coordinates: every rank rasterises its own
+rows (halo rows included), no exchange.  Halo rows are recomputed redundantly from the same
+inputs in the same order, so the result is bit-identical to the single-GPU run.
+
+``SlabSimulator`` is engine-agnostic host logic: the CUDA engine below drives
+libnatrix_b200.so slab handles; tests drive it with a CPU engine over gloo.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+DEFAULT_HALO = 24
+
+
+def partition_rows(height: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous (row0, rows) per rank; the first ``height % world`` ranks get one extra row."""
+    base, extra = divmod(height, world)
+    out, r = [], 0
+    for i in range(world):
+        n = base + (1 if i < extra else 0)
+        out.append((r, n))
+        r += n
+    return out
+
+
+class CudaSlabEngine:
+    """One slab handle of libnatrix_b200.so plus torch views of its halo regions."""
+
+    def __init__(self, width, height, row0, rows, halo, device):
+        import torch
+
+        from natrix_b200 import _lib as L
+        from natrix_b200.core.fluid_simulator import FluidSimulator
+
+        self.torch, self.L = torch, L
+        self.sim = FluidSimulator(width, height, None, device=device, slab=(row0, rows, halo))
+        self.device = device
+        self.stream = torch.cuda.ExternalStream(self.sim.cuda_stream, device=device)
+
+    FIELD_IDS = {"velocity": 0, "pressure": 1, "divergence": 2, "nbmask": 5}
+
+    def phase(self, phase: int, dt: float, sweeps: int = 0):
+        if phase == 0:
+            self.sim._push_params()
+        self.L.check(self.sim._lib.natrix_step_phase(self.sim._handle(), phase, dt, sweeps))
+
+    def rows_needed(self, phase: int, dt: float) -> int:
+        return self.L.check(self.sim._lib.natrix_halo_rows_needed(self.sim._handle(), phase, dt))
+
+    def halo_region(self, field: str, side: int, rows: int):
+        send, recv, nbytes = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        self.L.check(self.sim._lib.natrix_halo_region(self.sim._handle(), self.FIELD_IDS[field], side, rows,
+                                                      C.byref(send), C.byref(recv), C.byref(nbytes)))
+        return self._view(send.value, nbytes.value), self._view(recv.value, nbytes.value)
+
+    def _view(self, ptr: int, nbytes: int):
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
+                                        "strides": None}
+        return self.torch.as_tensor(_Raw(), device=f"cuda:{self.device}")
+
+    def stream_context(self):
+        return self.torch.cuda.stream(self.stream)
+
+
+class SlabSimulator:
+    """The reference's FluidSimulator surface for one rank's slab of a global grid."""
+
+    def __init__(self, width: int, height: int, engine=None, halo: int = DEFAULT_HALO, device: Optional[int] = None,
+                 group=None, depth: int = 8):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.width, self.height = int(width), int(height)
+        self.row0, self.rows = partition_rows(self.height, self.world)[self.rank]
+        self.halo = int(halo)
+        if self.rows < self.halo:
+            raise ValueError(f"slab of {self.rows} rows is shorter than its halo ({self.halo})")
+        if engine is None:
+            dev = int(os.environ.get("LOCAL_RANK", "0")) if device is None else device
+            engine = CudaSlabEngine(self.width, self.height, self.row0, self.rows, self.halo, dev)
+        self.engine = engine
+        self.depth = int(depth)
+        self.iterations = 50
+        self.simulate = True
+        self.exchanges = 0
+        self.exchanged_bytes = 0
+
+    # -- the reference's mutators, forwarded to the slab (global normalised coordinates)
+    @property
+    def sim(self):
+        return self.engine.sim
+
+    def add_velocity(self, position, velocity, radius):
+        if self.simulate:
+            self.sim.add_velocity(position, velocity, radius)
+
+    def add_circle_obstacle(self, position, radius, static=False):
+        if self.simulate:
+            self.sim.add_circle_obstacle(position, radius, static)
+
+    def add_triangle_obstacle(self, p1, p2, p3, static=False):
+        if self.simulate:
+            self.sim.add_triangle_obstacle(p1, p2, p3, static)
+
+    # -- halo exchange with the two neighbouring ranks
+    def exchange(self, field: str, rows: int):
+        if rows <= 0 or self.world == 1:
+            return
+        if rows > self.halo:
+            raise ValueError(f"{field}: step needs {rows} halo rows but the slab was created with {self.halo}")
+        dist = self.dist
+        ops, keep = [], []
+        up, down = self.rank - 1, self.rank + 1
+        ctx = self.engine.stream_context()
+        with ctx:
+            if up >= 0:
+                send, recv = self.engine.halo_region(field, 0, rows)
+                ops += [dist.P2POp(dist.isend, send, up, self.group), dist.P2POp(dist.irecv, recv, up, self.group)]
+                keep += [send, recv]
+            if down < self.world:
+                send, recv = self.engine.halo_region(field, 1, rows)
+                ops += [dist.P2POp(dist.isend, send, down, self.group), dist.P2POp(dist.irecv, recv, down, self.group)]
+                keep += [send, recv]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        self.exchanges += 1
+        self.exchanged_bytes += sum(t.numel() * t.element_size() for t in keep) // 2
+
+    # -- one step (ref: FluidSimulator.update, fluid_simulator.py:174-280) in four phases
+    def update(self, time_delta: float):
+        if not self.simulate:
+            return
+        e = self.engine
+        self.exchange("velocity", e.rows_needed(0, time_delta))
+        e.phase(0, time_delta)
+        e.phase(1, time_delta)
+        left, first = int(self.iterations), True
+        while left > 0:
+            t = min(self.depth, left)
+            if first:
+                self.exchange("divergence", self.depth)
+                self.exchange("nbmask", self.depth)
+            else:
+                self.exchange("pressure", t)
+            e.phase(2, time_delta, t)
+            left -= t
+            first = False
+        self.exchange("pressure", 1)
+        e.phase(3, time_delta)
+
+
+# ----------------------------------------------------------------------------------------- bench
+def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
+    """bench.py --gpus N under torchrun: weak scaling, one 32768 x 4096 slab per rank."""
+    import json
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    from natrix_b200 import _lib as L
+    from natrix_b200 import workloads as W
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    depth = args.depth or 8
+    slab = SlabSimulator(w.width, w.height, device=local, depth=depth)
+    sim = slab.sim
+    sim.vorticity, sim.viscosity, sim.iterations = w.vorticity, w.viscosity, w.iterations
+    slab.iterations = w.iterations
+    if args.pipeline is not None:
+        sim.set_option(L.OPT_PIPELINE, args.pipeline)
+    sim.set_option(L.OPT_JACOBI_DEPTH, depth)
+    sim.upload("velocity", W.smooth_velocity(w.width, w.height, slab.row0, slab.rows))
+
+    def one_step(k):
+        for (px, py, r) in w.circles:
+            slab.add_circle_obstacle((px, py), r)
+        slab.update(W.DT)
+        for (px, py, vx, vy) in W.orbit_positions(w, k):
+            slab.add_velocity((px, py), (vx, vy), w.splat_radius)
+
+    stream = slab.engine.stream
+    step = 0
+    for _ in range(max(args.warmup, 3)):
+        one_step(step); step += 1
+    sim.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = sim.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        one_step(step); step += 1
+    sim.synchronize()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=f"cuda:{local}")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    launches = sim.launch_count - launches0
+    ms_per_step = total_ms / args.steps
+    value = w.cells / (ms_per_step * 1e-3) / 1e6
+
+    # e2e: per-step host sync and readback of a velocity statistic on every rank
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step(step); step += 1
+        sim.stats("velocity")
+    dist.barrier()
+    e2e_ms = torch.tensor([1e3 * (time.perf_counter() - t0) / args.steps], device=f"cuda:{local}")
+    dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # the 1-GPU point of the same weak-scaling series, measured on this box: every rank runs the
+    # 32768 x 4096 grid standalone (no exchange); max over ranks
+    from natrix_b200.core.fluid_simulator import FluidSimulator
+    w1 = W.cfg5_workload(1, width=w.width, rows_per_gpu=slab.rows)
+    solo, _ = W.build(w1, FluidSimulator, None, device=local)
+    solo.set_option(L.OPT_JACOBI_DEPTH, depth)
+    sstream = torch.cuda.ExternalStream(solo.cuda_stream, device=local)
+    for k in range(2):
+        W.run_step(w1, solo, None, k)
+    solo.synchronize()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nb = max(3, min(args.steps, 5))
+    b0.record(sstream)
+    for k in range(nb):
+        W.run_step(w1, solo, None, 2 + k)
+    solo.synchronize()
+    b1.record(sstream)
+    torch.cuda.synchronize()
+    bms = torch.tensor([b0.elapsed_time(b1) / nb], device=f"cuda:{local}")
+    dist.all_reduce(bms, op=dist.ReduceOp.MAX)
+    base_value = w1.cells / (float(bms.item()) * 1e-3) / 1e6
+    solo.destroy()
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        algo = jacobi_bytes * w.cells * w.iterations + (116 if w.viscosity == 0 else 132) * w.cells
+        line = {
+            "metric": metric, "value": value, "unit": metric, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w.name, "grid": [w.width, w.height], "per_gpu_grid": [w.width, slab.rows],
+                       "jacobi_iterations": w.iterations, "obstacles_per_step": len(w.circles),
+                       "parallelism": f"row-slabs x{world}, halo {slab.halo} rows, NCCL send/recv",
+                       "jacobi_depth": depth, "l2": "per-GPU state 4.6 GB exceeds L2; no flush needed",
+                       "algorithmic_GBps_per_gpu": algo / world / (ms_per_step * 1e-3) / 1e9},
+            "weak_base": {"workload": w1.name, "n_gpus": 1, "value": base_value, "ms_per_step": float(bms.item()),
+                          "note": "same per-GPU slab run standalone on every rank of this box (max over ranks)"},
+            "halo": {"exchanges_per_step": slab.exchanges / (3 * args.steps + max(args.warmup, 3)),
+                     "bytes_per_step_per_neighbour": slab.exchanged_bytes / max(slab.exchanges, 1)},
+            "e2e": {"value": w.cells / (float(e2e_ms.item()) * 1e-3) / 1e6, "unit": metric,
+                    "ms_per_step": float(e2e_ms.item()), "h2d_bytes_per_step": 16 * len(w.circles) + 32,
+                    "d2h_bytes_per_step": 32},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "cpu_baseline": None,
+            "peak_hbm_gbs": peak, "peak_source": peak_src,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0
