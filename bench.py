@@ -179,6 +179,8 @@ def run_single_gpu(args, w: W.Workload):
         sim.set_option(L.OPT_PIPELINE, args.pipeline)
     if args.depth is not None:
         sim.set_option(L.OPT_JACOBI_DEPTH, args.depth)
+    if args.packed is not None:
+        sim.set_option(L.OPT_PACKED, args.packed)
     sim.set_option(L.OPT_TIMING, 1)
     stream = torch.cuda.ExternalStream(sim.cuda_stream, device=dev)
 
@@ -280,6 +282,8 @@ def main(argv=None):
     ap.add_argument("--size", type=int, default=None, help="override the grid size of cfg3/cfg4")
     ap.add_argument("--pipeline", type=int, default=None)
     ap.add_argument("--depth", type=int, default=None)
+    ap.add_argument("--packed", type=int, default=None, help="0/1: f32x2 arithmetic in the Jacobi kernel")
+    ap.add_argument("--no-obstacles", action="store_true", help="diagnostic: drop the per-step obstacles")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args(argv)
 
@@ -299,6 +303,9 @@ def main(argv=None):
     else:
         w = W.cfg5_workload(n)
 
+    if args.no_obstacles:
+        w.circles = []
+        w.name += "-noobst"
     if args.impl == "reference":
         if name == "cfg5":          # keep the CPU arm bounded: the 1-GPU slab of the weak-scaling grid
             w = W.cfg5_workload(1)

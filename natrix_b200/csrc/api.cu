@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -58,9 +59,10 @@ struct natrix_sim {
     int pipeline = 1, jacobi_depth = 8, timing = 0, graph = 0, packed = 1;
     // bookkeeping
     std::vector<SplatV> pending;                 // add_velocity calls not yet applied (pipeline 1)
-    bool obs_dirty = false, p_is_zero = false;
-    int* d_err = nullptr;
+    bool obs_dirty = false, p_is_zero = false, fused_pre = false;
+    int* d_err = nullptr;                        // [0] advection left the slab's halo, [1] some |v| > 1 in the READ velocity
     int* h_err = nullptr;
+    int sm_count = 148;
     double *d_scratch = nullptr, *d_out4 = nullptr, *h_out4 = nullptr;
     float2* d_tmp2 = nullptr;                    // staging for OBSTACLES copy in/out
     unsigned long long launches = 0;
@@ -108,13 +110,24 @@ void stamp(natrix_sim* s, int i) {
 // apply queued add_velocity calls in one pass (pipeline 1) - identical per-cell arithmetic
 int flush_splats(natrix_sim* s) {
     size_t i = 0;
+    const int lo = s->ext_lo(s->g.halo), hi = s->ext_hi(s->g.halo);
     while (i < s->pending.size()) {
-        SplatVBatch b;
-        b.n = 0;
-        while (i < s->pending.size() && b.n < MAX_SPLATS) b.s[b.n++] = s->pending[i++];
-        s->launches += launch_add_velocity(s->vel[s->vr], s->vel[1 - s->vr], s->g, s->ext_lo(s->g.halo),
-                                           s->ext_hi(s->g.halo), b, s->st);
-        s->vr = 1 - s->vr;
+        if (s->pipeline == 0) {
+            // one full-grid dispatch + ping-pong flip per call, like the reference
+            SplatVBatch b;
+            b.n = 1;
+            b.s[0] = s->pending[i++];
+            s->launches += launch_add_velocity(s->vel[s->vr], s->vel[1 - s->vr], s->g, lo, hi, b, s->st);
+            s->vr = 1 - s->vr;
+        } else {
+            // up to MAX_SPLATS calls in one in-place pass over their bounding boxes; cells outside
+            // only need the all-cell clamp, and only if some |v| > 1 (d_err[1])
+            const int n = (int)std::min<size_t>(MAX_SPLATS, s->pending.size() - i);
+            s->launches += launch_splat_velocity_boxes(s->vel[s->vr], s->g, lo, hi, &s->pending[i], n, s->d_err + 1,
+                                                       s->sm_count, s->st);
+            CU(cudaMemsetAsync(s->d_err + 1, 0, sizeof(int), s->st));      // every |v| <= 1 now
+            i += n;
+        }
     }
     s->pending.clear();
     CU(cudaGetLastError());
@@ -125,11 +138,17 @@ int flush_dye(natrix_dye* d) {
     natrix_sim* s = d->sim;
     size_t i = 0;
     while (i < d->pending.size()) {
-        SplatDBatch b;
-        b.n = 0;
-        while (i < d->pending.size() && b.n < MAX_SPLATS) b.s[b.n++] = d->pending[i++];
-        s->launches += launch_dye_add(d->d[d->rd], d->d[1 - d->rd], d->w, d->h, b, s->st);
-        d->rd = 1 - d->rd;
+        if (s->pipeline == 0) {
+            SplatDBatch b;
+            b.n = 1;
+            b.s[0] = d->pending[i++];
+            s->launches += launch_dye_add(d->d[d->rd], d->d[1 - d->rd], d->w, d->h, b, s->st);
+            d->rd = 1 - d->rd;
+        } else {
+            const int n = (int)std::min<size_t>(MAX_SPLATS, d->pending.size() - i);
+            s->launches += launch_splat_dye_boxes(d->d[d->rd], d->w, d->h, &d->pending[i], n, s->st);
+            i += n;
+        }
     }
     d->pending.clear();
     CU(cudaGetLastError());
@@ -154,6 +173,17 @@ int phase_advect(natrix_sim* s, float dt) {
     if (int rc = flush_splats(s)) return rc;
     stamp(s, ST_ADVECT);
     const bool fold = s->pipeline != 0 && s->has_borders;
+    s->fused_pre = s->pipeline != 0 && preproject_supported(g);
+    if (s->fused_pre) {
+        // advect + vorticity + confinement + [viscosity] + divergence + mask in one pass; the
+        // velocity buffer flips once (the intermediate velocities never reach memory)
+        s->launches += launch_preproject(s->vel[s->vr], s->obs, s->vel[1 - s->vr], s->vort, s->div, s->nbm, g, 0, g.hl,
+                                         dt, s->speed, s->dissipation, s->vorticity, s->viscous != 0, s->alpha,
+                                         s->rbeta, fold, s->sm_count, s->d_err, s->st);
+        s->vr = 1 - s->vr;
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (s->has_borders && !fold)
         s->launches += launch_init_boundaries(s->vel[s->vr], g, s->ext_lo(g.halo), s->ext_hi(g.halo), s->st);
     s->launches += launch_advect(s->vel[s->vr], s->obs, s->vel[1 - s->vr], g, s->ext_lo(4), s->ext_hi(4), dt,
@@ -166,6 +196,13 @@ int phase_advect(natrix_sim* s, float dt) {
 int phase_forces(natrix_sim* s, float dt) {
     const Geom& g = s->g;
     stamp(s, ST_VORT);
+    if (s->fused_pre) {
+        stamp(s, ST_DIV);
+        CU(cudaMemsetAsync(s->p_base[s->pr], 0, s->cells_alloc * sizeof(float), s->st));
+        s->launches += 1;
+        s->p_is_zero = true;
+        return 0;
+    }
     s->launches += launch_vorticity(s->vel[s->vr], s->vort, g, s->ext_lo(3), s->ext_hi(3), s->st);
     s->launches += launch_confinement(s->vel[s->vr], s->vort, s->vel[1 - s->vr], g, s->ext_lo(2), s->ext_hi(2),
                                       dt, s->vorticity, s->st);
@@ -223,7 +260,8 @@ int phase_project(natrix_sim* s) {
     if (s->pipeline == 0)
         s->launches += launch_gradient_ref(s->vel[s->vr], s->p[s->pr], s->obs, s->vel[1 - s->vr], g, 0, g.hl, s->st);
     else
-        s->launches += launch_gradient_mask(s->vel[s->vr], s->p[s->pr], s->nbm, s->vel[1 - s->vr], g, 0, g.hl, s->st);
+        s->launches += launch_gradient_mask(s->vel[s->vr], s->p[s->pr], s->nbm, s->vel[1 - s->vr], g, 0, g.hl,
+                                            s->d_err + 1, s->st);
     s->vr = 1 - s->vr;
     stamp(s, ST_CLEAR);
     // clear obstacles (fluid_simulator.py:268-280); skipped when nothing was stamped since the
@@ -283,8 +321,9 @@ int natrix_create_slab(int width, int global_height, int row0, int rows, int hal
     if (e == cudaSuccess) e = alloc_rows(&s->vort_base, &s->vort, s);
     if (e == cudaSuccess) e = alloc_rows(&s->obs_base, &s->obs, s);
     if (e == cudaSuccess) e = alloc_rows(&s->nbm_base, &s->nbm, s);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_err, sizeof(int));
-    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_err, 0, sizeof(int), s->st);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_err, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_err, 0, 2 * sizeof(int), s->st);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_err, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_scratch, 4 * 1024 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_out4, 4 * sizeof(double));
@@ -349,6 +388,7 @@ int natrix_set_option(natrix_sim* s, int option, int value) {
         NEED(value == 0 || value == 1, "pipeline must be 0 or 1");
         if (int rc = select_device(s)) return rc;
         if (int rc = flush_splats(s)) return rc;
+        CU(cudaMemsetAsync(s->d_err + 1, 1, sizeof(int), s->st));   // pipeline 0 does not track |v| > 1
         s->pipeline = value; return 0;
     case NATRIX_OPT_JACOBI_DEPTH:
         NEED(value >= 1 && value <= JACOBI_TB_MAX_DEPTH, "jacobi depth out of range");
@@ -534,6 +574,7 @@ int natrix_copy_in(natrix_sim* s, int field, const void* host, size_t bytes) {
     CU(cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, s->st));
     CU(cudaStreamSynchronize(s->st));
     if (field == NATRIX_PRESSURE) s->p_is_zero = false;
+    if (field == NATRIX_VELOCITY) CU(cudaMemsetAsync(s->d_err + 1, 1, sizeof(int), s->st));   // unknown range
     return 0;
 }
 

@@ -61,6 +61,64 @@ __device__ __forceinline__ Corners corners(float fx, float fy, int w, int h) {
     return c;
 }
 
+__device__ __forceinline__ ptrdiff_t lin(const Geom& g, int x, int ly) {
+    return (ptrdiff_t)ly * g.w + x;
+}
+
+// Velocity load with shader.InitBoundaries.comp:14-34 folded in when FOLD: the four border lines
+// of the READ buffer read as zero (the in-place zeroing is not observable after the step).
+template <bool FOLD>
+__device__ __forceinline__ float2 load_vel(const float2* __restrict__ v, const Geom& g, int x, int gy) {
+    if (FOLD && (x == 0 || x == g.w - 1 || gy == 0 || gy == g.hg - 1)) return make_float2(0.0f, 0.0f);
+    return v[lin(g, x, gy - g.y0)];
+}
+
+// ref: shader.AdvectVelocity.comp:36-49 for one non-solid cell (x, gy); reports gathers that leave the
+// rows this slab holds through *err (multi-GPU only; the full grid can never trip it)
+template <bool FOLD>
+__device__ __forceinline__ float2 advect_cell(const float2* __restrict__ vin, const Geom& g, int x, int gy,
+                                              float2 vel, float dt, float speed, float diss, int* __restrict__ err) {
+    const float fx = (float)x - vel.x * dt * speed;
+    const float fy = (float)gy - vel.y * dt * speed;
+    Corners c = corners(fx, fy, g.w, g.hg);
+    const int lo = g.y0 - g.halo, hi = g.y0 + g.hl + g.halo - 1;
+    if (c.by < lo || c.ty > hi) {
+        *err = 1;
+        c.by = clampi(c.by, lo, hi);
+        c.ty = clampi(c.ty, lo, hi);
+    }
+    const float2 lt = load_vel<FOLD>(vin, g, c.bx, c.ty);
+    const float2 rt = load_vel<FOLD>(vin, g, c.tx, c.ty);
+    const float2 lb = load_vel<FOLD>(vin, g, c.bx, c.by);
+    const float2 rb = load_vel<FOLD>(vin, g, c.tx, c.by);
+    const float h1x = mixf(lt.x, rt.x, c.dx), h1y = mixf(lt.y, rt.y, c.dx);
+    const float h2x = mixf(lb.x, rb.x, c.dx), h2y = mixf(lb.y, rb.y, c.dx);
+    float2 o;
+    o.x = clampf(mixf(h2x, h1x, c.dy) * diss, -1.0f, 1.0f);
+    o.y = clampf(mixf(h2y, h1y, c.dy) * diss, -1.0f, 1.0f);
+    return o;
+}
+
+// ref: shader.ApplyVorticity.comp:33-39 - the confinement force times dt for one cell
+__device__ __forceinline__ float2 confinement_force(float wL, float wR, float wB, float wT, float wC, float scale,
+                                                    float dt) {
+    float fx = 0.5f * (fabsf(wT) - fabsf(wB));
+    float fy = 0.5f * (fabsf(wR) - fabsf(wL));
+    const float m = fmaxf(2.4414e-4f, fx * fx + fy * fy);
+    const float inv = 1.0f / sqrtf(m);
+    fx = fx * inv;
+    fy = fy * inv;
+    const float k = scale * wC;
+    fx = fx * k;
+    fy = fy * (-k);
+    return make_float2(fx * dt, fy * dt);
+}
+
+// m ? a : b for m all-ones / all-zero, without occupying a predicate register
+__device__ __forceinline__ float bitsel(float a, float b, uint32_t m) {
+    return __uint_as_float((__float_as_uint(a) & m) | (__float_as_uint(b) & ~m));
+}
+
 // streaming global accesses: data touched once per kernel should not pollute L1
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     float4 r;

@@ -6,15 +6,15 @@
 namespace natrix {
 namespace {
 
-constexpr int BX = 256;
+constexpr int BX = 64, BY = 4, BT = BX * BY;   // 2-D blocks: back-traced gathers of nearby rows hit L1
 
 // K splats applied in sequence per cell: identical arithmetic to K AddParticle dispatches
 // (each dispatch is a pure per-cell map, the ping-pong flip carries no cross-cell dependency).
-__global__ void __launch_bounds__(BX)
+__global__ void __launch_bounds__(BT)
 k_dye_add(const float* __restrict__ din, float* __restrict__ dout, int pw, int ph,
           const __grid_constant__ SplatDBatch b) {
     const int x = blockIdx.x * BX + threadIdx.x;
-    const int y = blockIdx.y;
+    const int y = blockIdx.y * BY + threadIdx.y;
     if (x >= pw || y >= ph) return;
     const size_t pos = (size_t)y * pw + x;
     float v = din[pos];
@@ -28,12 +28,12 @@ k_dye_add(const float* __restrict__ din, float* __restrict__ dout, int pw, int p
     dout[pos] = v;
 }
 
-__global__ void __launch_bounds__(BX)
+__global__ void __launch_bounds__(BT)
 k_dye_advect(const float* __restrict__ din, float* __restrict__ dout, int pw, int ph,
              const float2* __restrict__ vel, const uint8_t* __restrict__ obs, int vw, int vh,
              float dt, float speed, float diss) {
     const int x = blockIdx.x * BX + threadIdx.x;
-    const int y = blockIdx.y;
+    const int y = blockIdx.y * BY + threadIdx.y;
     if (x >= pw || y >= ph) return;
     const size_t pos = (size_t)y * pw + x;
     // fNormalisedPos (:46) and the obstacle lookup at its truncation (:47-50)
@@ -60,14 +60,14 @@ k_dye_advect(const float* __restrict__ din, float* __restrict__ dout, int pw, in
 }  // namespace
 
 int launch_dye_add(const float* din, float* dout, int pw, int ph, const SplatDBatch& b, cudaStream_t st) {
-    dim3 grid((pw + BX - 1) / BX, ph, 1);
-    k_dye_add<<<grid, BX, 0, st>>>(din, dout, pw, ph, b);
+    dim3 grid((pw + BX - 1) / BX, (ph + BY - 1) / BY, 1);
+    k_dye_add<<<grid, dim3(BX, BY, 1), 0, st>>>(din, dout, pw, ph, b);
     return 1;
 }
 int launch_dye_advect(const float* din, float* dout, int pw, int ph, const float2* vel, const uint8_t* obs,
                       int vw, int vh, float dt, float speed, float diss, cudaStream_t st) {
-    dim3 grid((pw + BX - 1) / BX, ph, 1);
-    k_dye_advect<<<grid, BX, 0, st>>>(din, dout, pw, ph, vel, obs, vw, vh, dt, speed, diss);
+    dim3 grid((pw + BX - 1) / BX, (ph + BY - 1) / BY, 1);
+    k_dye_advect<<<grid, dim3(BX, BY, 1), 0, st>>>(din, dout, pw, ph, vel, obs, vw, vh, dt, speed, diss);
     return 1;
 }
 

@@ -1,0 +1,421 @@
+// fused.cu - the fused pipeline's non-Jacobi kernels (NATRIX_OPT_PIPELINE = 1).
+//
+//  * k_preproject: ONE pass for everything the reference does between the start of update() and the
+//    Poisson loop - [InitBoundaries] -> AdvectVelocity -> CalcVorticity -> ApplyVorticity ->
+//    [Viscosity] -> Divergence (+ the blocked-neighbour mask).  Reads velocity 8 B + obstacles 1 B per
+//    cell, writes velocity 8 B, vorticity 4 B, divergence 4 B, mask 1 B = 26 B/cell, instead of
+//    92 B/cell (108 with viscosity) for the five dispatches.
+//  * impulse kernels that touch only the bounding boxes of the splats, in place;
+//  * the gradient subtraction driven by the mask.
+//
+// All of them produce bit-identical results to the one-kernel-per-shader versions in
+// stages_ref.cu (same expressions, same operand order, -fmad=false).
+#include "kernels.h"
+
+namespace natrix {
+namespace {
+
+// ------------------------------------------------------------------------------------ pre-projection
+//
+// Streaming decomposition (same idea as jacobi_tb.cu): one warp owns a strip of 128 columns (4 per
+// lane, 4 halo columns on each side recomputed) and marches down its chunk of rows.  When the
+// advected row `ly` is produced, the vorticity of row ly-1, the confined velocity of row ly-2,
+// [the viscous velocity of row ly-3] and the divergence of the row above that follow from rolling
+// 3-row windows held in registers; left/right neighbours come from the adjacent lanes by shuffle.
+constexpr int PSW = 128;      // strip width
+constexpr int PHX = 4;        // halo columns per side = number of x-neighbour stages
+constexpr int PWARPS = 8;
+
+struct PreParams {
+    int r0, r1;               // output rows (local)
+    int ch, nstrips, ntiles;
+    float dt, speed, diss, scale, alpha, rbeta;
+};
+
+__device__ __forceinline__ void copy4(float2 (&d)[4], const float2 (&s)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[j] = s[j];
+}
+__device__ __forceinline__ void copy4(float (&d)[4], const float (&s)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[j] = s[j];
+}
+
+template <bool VISCOUS, bool FOLD>
+__global__ void __launch_bounds__(PWARPS * 32, 2)
+k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, float2* __restrict__ vout,
+             float* __restrict__ vort, float* __restrict__ div, uint8_t* __restrict__ nbmask, const Geom g,
+             const PreParams prm, int* __restrict__ err) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int DEPTH = VISCOUS ? 4 : 3;            // rows between the advected row and the divergence row
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * PWARPS + warp;
+    if (tile >= prm.ntiles) return;
+    const int chunk = tile / prm.nstrips, strip = tile - chunk * prm.nstrips;
+    const int x0 = strip * (PSW - 2 * PHX) - PHX;
+    const int xa = x0 + 4 * lane;                      // first of this lane's 4 columns (multiple of 4)
+    const int out_lo = prm.r0 + chunk * prm.ch;
+    const int out_hi = min(out_lo + prm.ch, prm.r1);
+    const bool inside = xa >= 0 && xa + 3 < g.w;      // all 4 columns are grid columns
+    const bool st_ok = 4 * lane >= PHX && 4 * lane < PSW - PHX && inside;
+    const uint32_t edge_l = xa == 0 ? 0xffffffffu : 0u, edge_r = xa + 4 == g.w ? 0xffffffffu : 0u;
+    const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
+    const int xc0 = clampi(xa, 0, g.w - 4);            // clamped column group for memory safety (halo lanes)
+
+    float2 A0[4], A1[4], B0[4], B1[4], C0[4], C1[4];   // older / newer kept rows of each stage
+    float W0[4], W1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        A0[j] = A1[j] = B0[j] = B1[j] = C0[j] = C1[j] = make_float2(0.0f, 0.0f);
+        W0[j] = W1[j] = 0.0f;
+    }
+
+    for (int ly = out_lo - DEPTH; ly < out_hi + DEPTH; ++ly) {
+        const int gy = g.y0 + ly;
+        // ---- stage 0: advect row ly (ref: shader.AdvectVelocity.comp:27-50, borders folded in)
+        float2 An[4];
+        if (gy >= 0 && gy < g.hg) {
+            const ptrdiff_t base = lin(g, xc0, ly);
+            const uint32_t ow = *reinterpret_cast<const uint32_t*>(obs + base);
+            const float4 c01 = *reinterpret_cast<const float4*>(vin + base);
+            const float4 c23 = *reinterpret_cast<const float4*>(vin + base + 2);
+            const float2 cv[4] = {make_float2(c01.x, c01.y), make_float2(c01.z, c01.w), make_float2(c23.x, c23.y),
+                                  make_float2(c23.z, c23.w)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int x = xc0 + j;
+                if ((ow >> (8 * j)) & 0xffu) {
+                    An[j] = make_float2(0.0f, 0.0f);
+                } else {
+                    float2 v = cv[j];
+                    if (FOLD && (x == 0 || x == g.w - 1 || gy == 0 || gy == g.hg - 1)) v = make_float2(0.0f, 0.0f);
+                    An[j] = advect_cell<FOLD>(vin, g, x, gy, v, prm.dt, prm.speed, prm.diss, err);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) An[j] = make_float2(0.0f, 0.0f);
+        }
+
+        // ---- stage 1: vorticity of row r1 = ly-1 (ref: shader.CalcVorticity.comp:20-26)
+        // clamp-to-edge in y: at the first / last grid row the missing neighbour row is the row itself
+        const int r1 = ly - 1, g1 = gy - 1;
+        if (g1 == 0) copy4(A0, A1);
+        if (g1 == g.hg - 1) copy4(An, A1);
+        float Wn[4];
+        {
+            const float ly_ = bitsel(A1[0].y, __shfl_sync(FULL, A1[3].y, lane_l), edge_l);
+            const float ry_ = bitsel(A1[3].y, __shfl_sync(FULL, A1[0].y, lane_r), edge_r);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float vLy = j > 0 ? A1[j - 1].y : ly_;
+                const float vRy = j < 3 ? A1[j + 1].y : ry_;
+                Wn[j] = 0.5f * ((vRy - vLy) - (An[j].x - A0[j].x));
+            }
+            if (st_ok && r1 >= out_lo && r1 < out_hi)
+                stg_stream(reinterpret_cast<float4*>(vort + lin(g, xa, r1)), make_float4(Wn[0], Wn[1], Wn[2], Wn[3]));
+        }
+
+        // ---- stage 2: confinement on row r2 = ly-2 (ref: shader.ApplyVorticity.comp:26-39)
+        const int g2 = gy - 2;
+        if (g2 == 0) copy4(W0, W1);
+        if (g2 == g.hg - 1) copy4(Wn, W1);
+        float2 Bn[4];
+        {
+            const float wl = bitsel(W1[0], __shfl_sync(FULL, W1[3], lane_l), edge_l);
+            const float wr = bitsel(W1[3], __shfl_sync(FULL, W1[0], lane_r), edge_r);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float wL = j > 0 ? W1[j - 1] : wl;
+                const float wR = j < 3 ? W1[j + 1] : wr;
+                const float2 f = confinement_force(wL, wR, W0[j], Wn[j], W1[j], prm.scale, prm.dt);
+                Bn[j] = make_float2(A0[j].x + f.x, A0[j].y + f.y);      // A0 is row ly-2 here
+            }
+        }
+
+        // ---- stage 3 (optional): viscosity on row r3 = ly-3 (ref: shader.Viscosity.comp:24-31)
+        float2 Fn[4];           // newest row of the final pre-projection velocity
+        int rF;                 // its local row
+        if (VISCOUS) {
+            const int g3 = gy - 3;
+            if (g3 == 0) copy4(B0, B1);
+            if (g3 == g.hg - 1) copy4(Bn, B1);
+            const float lx = bitsel(B1[0].x, __shfl_sync(FULL, B1[3].x, lane_l), edge_l);
+            const float ly2 = bitsel(B1[0].y, __shfl_sync(FULL, B1[3].y, lane_l), edge_l);
+            const float rx = bitsel(B1[3].x, __shfl_sync(FULL, B1[0].x, lane_r), edge_r);
+            const float ry = bitsel(B1[3].y, __shfl_sync(FULL, B1[0].y, lane_r), edge_r);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 x1 = j > 0 ? B1[j - 1] : make_float2(lx, ly2);
+                const float2 x2 = j < 3 ? B1[j + 1] : make_float2(rx, ry);
+                Fn[j].x = (x1.x + x2.x + B0[j].x + Bn[j].x + B1[j].x * prm.alpha) * prm.rbeta;
+                Fn[j].y = (x1.y + x2.y + B0[j].y + Bn[j].y + B1[j].y * prm.alpha) * prm.rbeta;
+            }
+            rF = ly - 3;
+        } else {
+            copy4(Fn, Bn);
+            rF = ly - 2;
+        }
+        if (st_ok && rF >= out_lo && rF < out_hi) {
+            float4* dst = reinterpret_cast<float4*>(vout + lin(g, xa, rF));
+            stg_stream(dst, make_float4(Fn[0].x, Fn[0].y, Fn[1].x, Fn[1].y));
+            stg_stream(dst + 1, make_float4(Fn[2].x, Fn[2].y, Fn[3].x, Fn[3].y));
+        }
+
+        // ---- stage 4: divergence + blocked-neighbour mask of row rd = rF-1
+        //      (ref: shader.Divergence.comp:22-40; mask bits as in stages_ref.cu k_divergence)
+        float2 (&F0)[4] = VISCOUS ? C0 : B0;      // row rd-1
+        float2 (&F1)[4] = VISCOUS ? C1 : B1;      // row rd
+        const int rd = rF - 1, gd = g.y0 + rd;
+        if (rd >= out_lo && rd < out_hi) {
+            if (gd == 0) copy4(F0, F1);
+            if (gd == g.hg - 1) copy4(Fn, F1);
+            const uint32_t oM = *reinterpret_cast<const uint32_t*>(obs + lin(g, xc0, rd));
+            const uint32_t oB = *reinterpret_cast<const uint32_t*>(obs + lin(g, xc0, max(gd - 1, 0) - g.y0));
+            const uint32_t oT = *reinterpret_cast<const uint32_t*>(obs + lin(g, xc0, min(gd + 1, g.hg - 1) - g.y0));
+            const uint32_t oLw = __shfl_sync(FULL, oM, lane_l), oRw = __shfl_sync(FULL, oM, lane_r);
+            const uint32_t oL = edge_l ? (oM & 0xffu) : (oLw >> 24);          // obstacle byte of column xa-1
+            const uint32_t oR = edge_r ? (oM >> 24) : (oRw & 0xffu);          // obstacle byte of column xa+4
+            const float lx = bitsel(F1[0].x, __shfl_sync(FULL, F1[3].x, lane_l), edge_l);
+            const float rx = bitsel(F1[3].x, __shfl_sync(FULL, F1[0].x, lane_r), edge_r);
+            float dv[4];
+            uint32_t mword = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool sL = (j > 0 ? (oM >> (8 * (j - 1))) & 0xffu : oL) != 0u;
+                const bool sR = (j < 3 ? (oM >> (8 * (j + 1))) & 0xffu : oR) != 0u;
+                const bool sB = ((oB >> (8 * j)) & 0xffu) != 0u;
+                const bool sT = ((oT >> (8 * j)) & 0xffu) != 0u;
+                const float x1 = sL ? 0.0f : (j > 0 ? F1[j - 1].x : lx);
+                const float x2 = sR ? 0.0f : (j < 3 ? F1[j + 1].x : rx);
+                const float y1 = sB ? 0.0f : F0[j].y;
+                const float y2 = sT ? 0.0f : Fn[j].y;
+                dv[j] = 0.5f * ((x2 - x1) + (y2 - y1));
+                const int x = xa + j;
+                uint32_t m = 0u;
+                if (sL || x == 0) m |= NB_L;
+                if (sR || x == g.w - 1) m |= NB_R;
+                if (sB || gd == 0) m |= NB_B;
+                if (sT || gd == g.hg - 1) m |= NB_T;
+                mword |= m << (8 * j);
+            }
+            if (st_ok) {
+                stg_stream(reinterpret_cast<float4*>(div + lin(g, xa, rd)), make_float4(dv[0], dv[1], dv[2], dv[3]));
+                *reinterpret_cast<uint32_t*>(nbmask + lin(g, xa, rd)) = mword;
+            }
+        }
+
+        // ---- roll the windows
+        copy4(A0, A1); copy4(A1, An);
+        copy4(W0, W1); copy4(W1, Wn);
+        copy4(B0, B1); copy4(B1, Bn);
+        if (VISCOUS) { copy4(C0, C1); copy4(C1, Fn); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- impulses
+constexpr int SBX = 64, SBY = 4;
+
+struct Box { int x0, x1, y0, y1; };                 // global cell coordinates, half-open
+struct SplatVBoxes { int n; SplatV s[MAX_SPLATS]; Box b[MAX_SPLATS]; };
+struct SplatDBoxes { int n; SplatD s[MAX_SPLATS]; Box b[MAX_SPLATS]; };
+
+__device__ __forceinline__ bool in_box(const Box& b, int x, int y) {
+    return x >= b.x0 && x < b.x1 && y >= b.y0 && y < b.y1;
+}
+
+// ref: shader.AddVelocity.comp:26-35, b.n dispatches applied in order, in place, to the cells inside
+// at least one splat's bounding box; the cell is handled by the block of the FIRST box containing it.
+__global__ void __launch_bounds__(SBX * SBY)
+k_splat_velocity_boxes(float2* __restrict__ vel, const Geom g, const __grid_constant__ SplatVBoxes b) {
+    const int i = blockIdx.z;
+    const Box bx = b.b[i];
+    const int x = bx.x0 + blockIdx.x * SBX + threadIdx.x;
+    const int gy = bx.y0 + blockIdx.y * SBY + threadIdx.y;
+    if (x >= bx.x1 || gy >= bx.y1) return;
+    for (int k = 0; k < i; ++k)
+        if (in_box(b.b[k], x, gy)) return;
+    const ptrdiff_t pos = lin(g, x, gy - g.y0);
+    float2 v = vel[pos];
+    const float fxp = (float)x, fyp = (float)gy;
+    for (int k = 0; k < b.n; ++k) {
+        const SplatV s = b.s[k];
+        const float ex = s.sx - fxp, ey = s.sy - fyp;
+        const float len = sqrtf(ex * ex + ey * ey);
+        if (len <= s.r) {
+            const float fall = s.r - len;
+            v.x = v.x + s.vx * fall / s.r;
+            v.y = v.y + s.vy * fall / s.r;
+        }
+        v.x = clampf(v.x, -1.0f, 1.0f);
+        v.y = clampf(v.y, -1.0f, 1.0f);
+    }
+    vel[pos] = v;
+}
+
+// The clamp that every AddVelocity dispatch applies to ALL cells, for the cells outside
+// every box.  It only has work to do if some |v| > 1, which the kernel that produced the field
+// recorded in *over1; otherwise every block leaves at once.
+__global__ void __launch_bounds__(256)
+k_clamp_outside_boxes(float2* __restrict__ vel, const Geom g, int r0, int r1, const __grid_constant__ SplatVBoxes b,
+                      const int* __restrict__ over1) {
+    if (*over1 == 0) return;
+    const size_t n = (size_t)(r1 - r0) * g.w;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int ly = r0 + (int)(i / g.w), x = (int)(i % g.w);
+        bool skip = false;
+        for (int k = 0; k < b.n; ++k) skip = skip || in_box(b.b[k], x, g.y0 + ly);
+        if (skip) continue;
+        float2 v = vel[lin(g, x, ly)];
+        v.x = clampf(v.x, -1.0f, 1.0f);
+        v.y = clampf(v.y, -1.0f, 1.0f);
+        vel[lin(g, x, ly)] = v;
+    }
+}
+
+// ref: demo/shaders/shader.AddParticle.comp:25-34, b.n dispatches in order, in place, boxes only
+__global__ void __launch_bounds__(SBX * SBY)
+k_splat_dye_boxes(float* __restrict__ dye, int pw, const __grid_constant__ SplatDBoxes b) {
+    const int i = blockIdx.z;
+    const Box bx = b.b[i];
+    const int x = bx.x0 + blockIdx.x * SBX + threadIdx.x;
+    const int y = bx.y0 + blockIdx.y * SBY + threadIdx.y;
+    if (x >= bx.x1 || y >= bx.y1) return;
+    for (int k = 0; k < i; ++k)
+        if (in_box(b.b[k], x, y)) return;
+    const size_t pos = (size_t)y * pw + x;
+    float v = dye[pos];
+    const float fxp = (float)x, fyp = (float)y;
+    for (int k = 0; k < b.n; ++k) {
+        const SplatD s = b.s[k];
+        const float ex = s.sx - fxp, ey = s.sy - fyp;
+        const float len = sqrtf(ex * ex + ey * ey);
+        if (len <= s.r) v = clampf(v + s.value * (s.r - len) / s.r, 0.0f, 255.0f);
+    }
+    dye[pos] = v;
+}
+
+// Cells with sqrt(ex^2 + ey^2) <= r lie within r + 2 of the centre along each axis (sqrt is monotone and
+// >= |ex| up to one rounding); clip to [xlo, xhi) x [ylo, yhi).  A negative or NaN radius selects nothing.
+Box splat_box(float sx, float sy, float r, int xlo, int xhi, int ylo, int yhi) {
+    Box b{0, 0, 0, 0};
+    if (!(r >= 0.0f)) return b;
+    const double m = (double)r + 2.0;
+    const double x0 = (double)sx - m, x1 = (double)sx + m, y0 = (double)sy - m, y1 = (double)sy + m;
+    if (!(x1 >= xlo && x0 <= xhi && y1 >= ylo && y0 <= yhi)) return b;     // also rejects NaN centres
+    b.x0 = x0 > xlo ? (int)x0 : xlo;
+    b.x1 = x1 < xhi - 1 ? (int)x1 + 1 : xhi;
+    b.y0 = y0 > ylo ? (int)y0 : ylo;
+    b.y1 = y1 < yhi - 1 ? (int)y1 + 1 : yhi;
+    if (b.x1 <= b.x0 || b.y1 <= b.y0) b = Box{0, 0, 0, 0};
+    return b;
+}
+
+template <class Boxes>
+dim3 boxes_grid(const Boxes& b) {
+    int mw = 0, mh = 0;
+    for (int i = 0; i < b.n; ++i) {
+        mw = b.b[i].x1 - b.b[i].x0 > mw ? b.b[i].x1 - b.b[i].x0 : mw;
+        mh = b.b[i].y1 - b.b[i].y0 > mh ? b.b[i].y1 - b.b[i].y0 : mh;
+    }
+    return dim3((mw + SBX - 1) / SBX, (mh + SBY - 1) / SBY, b.n);
+}
+
+// ------------------------------------------------------------------------------------------- gradient
+// ref: shader.SubtractGradient.comp:24-46 via the blocked-neighbour mask; also records whether any
+// |v| > 1 leaves the step (lets the next add_velocity skip its all-cell clamp pass).
+constexpr int GBX = 64, GBY = 4;
+__global__ void __launch_bounds__(GBX * GBY)
+k_gradient_mask(const float2* __restrict__ vin, const float* __restrict__ p, const uint8_t* __restrict__ nbmask,
+                float2* __restrict__ vout, const Geom g, int r0, int r1, int* __restrict__ over1) {
+    const int x = blockIdx.x * GBX + threadIdx.x;
+    const int ly = r0 + (int)blockIdx.y * GBY + threadIdx.y;
+    if (x >= g.w || ly >= r1) return;
+    const ptrdiff_t pos = lin(g, x, ly);
+    const uint8_t m = nbmask[pos];
+    const float c = p[pos];
+    const float x1 = (m & NB_L) ? c : p[pos - 1];
+    const float x2 = (m & NB_R) ? c : p[pos + 1];
+    const float y1 = (m & NB_B) ? c : p[pos - g.w];
+    const float y2 = (m & NB_T) ? c : p[pos + g.w];
+    float2 v = vin[pos];
+    v.x = v.x - 0.5f * (x2 - x1);
+    v.y = v.y - 0.5f * (y2 - y1);
+    vout[pos] = v;
+    if (fabsf(v.x) > 1.0f || fabsf(v.y) > 1.0f) *over1 = 1;
+}
+
+}  // namespace
+
+bool preproject_supported(const Geom& g) { return g.w % 4 == 0 && g.w >= 8; }
+
+int launch_preproject(const float2* vin, const uint8_t* obs, float2* vout, float* vort, float* div, uint8_t* nbmask,
+                      Geom g, int r0, int r1, float dt, float speed, float diss, float scale, bool viscous, float alpha,
+                      float rbeta, bool fold, int sm_count, int* err, cudaStream_t st) {
+    if (r1 <= r0) return 0;
+    PreParams prm;
+    prm.r0 = r0; prm.r1 = r1;
+    prm.dt = dt; prm.speed = speed; prm.diss = diss; prm.scale = scale; prm.alpha = alpha; prm.rbeta = rbeta;
+    prm.nstrips = (g.w + (PSW - 2 * PHX) - 1) / (PSW - 2 * PHX);
+    const int rows = r1 - r0;
+    int nchunks = (sm_count * PWARPS * 2) / prm.nstrips;        // one tile per resident warp
+    if (nchunks < 1) nchunks = 1;
+    int ch = (rows + nchunks - 1) / nchunks;
+    if (ch < 16) ch = 16;
+    prm.ch = ch;
+    nchunks = (rows + ch - 1) / ch;
+    prm.ntiles = prm.nstrips * nchunks;
+    const int blocks = (prm.ntiles + PWARPS - 1) / PWARPS;
+    if (viscous) {
+        if (fold) k_preproject<true, true><<<blocks, PWARPS * 32, 0, st>>>(vin, obs, vout, vort, div, nbmask, g, prm, err);
+        else k_preproject<true, false><<<blocks, PWARPS * 32, 0, st>>>(vin, obs, vout, vort, div, nbmask, g, prm, err);
+    } else {
+        if (fold) k_preproject<false, true><<<blocks, PWARPS * 32, 0, st>>>(vin, obs, vout, vort, div, nbmask, g, prm, err);
+        else k_preproject<false, false><<<blocks, PWARPS * 32, 0, st>>>(vin, obs, vout, vort, div, nbmask, g, prm, err);
+    }
+    return 1;
+}
+
+int launch_gradient_mask(const float2* vin, const float* p, const uint8_t* nbmask, float2* vout, Geom g, int r0, int r1,
+                         int* over1, cudaStream_t st) {
+    if (r1 <= r0) return 0;
+    dim3 grid((g.w + GBX - 1) / GBX, (r1 - r0 + GBY - 1) / GBY, 1);
+    k_gradient_mask<<<grid, dim3(GBX, GBY, 1), 0, st>>>(vin, p, nbmask, vout, g, r0, r1, over1);
+    return 1;
+}
+
+int launch_splat_velocity_boxes(float2* vel, Geom g, int r0, int r1, const SplatV* splats, int n, const int* over1,
+                                int sm_count, cudaStream_t st) {
+    if (n <= 0 || r1 <= r0) return 0;
+    SplatVBoxes b;
+    b.n = n;
+    for (int i = 0; i < n; ++i) {
+        b.s[i] = splats[i];
+        b.b[i] = splat_box(splats[i].sx, splats[i].sy, splats[i].r, 0, g.w, g.y0 + r0, g.y0 + r1);
+    }
+    int launched = 0;
+    k_clamp_outside_boxes<<<sm_count * 4, 256, 0, st>>>(vel, g, r0, r1, b, over1);
+    ++launched;
+    const dim3 grid = boxes_grid(b);
+    if (grid.x > 0 && grid.y > 0) {
+        k_splat_velocity_boxes<<<grid, dim3(SBX, SBY, 1), 0, st>>>(vel, g, b);
+        ++launched;
+    }
+    return launched;
+}
+
+int launch_splat_dye_boxes(float* dye, int pw, int ph, const SplatD* splats, int n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    SplatDBoxes b;
+    b.n = n;
+    for (int i = 0; i < n; ++i) {
+        b.s[i] = splats[i];
+        b.b[i] = splat_box(splats[i].sx, splats[i].sy, splats[i].r, 0, pw, 0, ph);
+    }
+    const dim3 grid = boxes_grid(b);
+    if (grid.x == 0 || grid.y == 0) return 0;
+    k_splat_dye_boxes<<<grid, dim3(SBX, SBY, 1), 0, st>>>(dye, pw, b);
+    return 1;
+}
+
+}  // namespace natrix

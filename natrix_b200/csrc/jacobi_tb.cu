@@ -16,9 +16,9 @@
 // result is bit-identical.
 //
 // Staging.  Input rows come through TMA (cp.async.bulk.tensor.2d, SASS UTMALDG): each warp runs
-// its own ring of 2-row x 128-column boxes for p (8 rows), div (16 rows: a div row is needed again by every
-// level for T more iterations) and the mask (8 rows), completed on 4 warp-private mbarriers and
-// issued 3 groups (6 rows) ahead by lane 0.  Out-of-bounds parts of a box (strip halos beyond the
+// its own ring of 4-row x 128-column boxes for p (8 rows), div (16 rows: a div row is needed again by every
+// level for T more iterations) and the mask (8 rows), completed on 2 warp-private mbarriers; lane 0 puts
+// the next box in flight as soon as the current one has landed.  Out-of-bounds parts of a box (strip halos beyond the
 // grid, rows beyond the slab) are zero-filled by TMA; those values only ever feed cells whose
 // results are discarded, because every in-domain cell next to the edge carries the "blocked"
 // bit for that direction and substitutes its own pressure (the shader's clamp-to-edge rule).
@@ -30,6 +30,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "jacobi_tb.h"
@@ -40,19 +41,25 @@ namespace natrix {
 namespace {
 
 constexpr int SW = 128;                 // strip width: columns per warp tile, 4 per lane
-constexpr int WARPS = 8;                // warps (= tiles) per block; 2 blocks per SM
-constexpr int P_ROWS = 8, M_ROWS = 8, D_ROWS = 16;
-constexpr int GROUP = 2;                // rows per TMA box
-constexpr int PD = 3;                   // groups issued ahead of consumption
-constexpr int NBAR = 4;                 // mbarriers per warp (PD in flight + 1 being consumed)
+// Launch shapes (V): 0 = 8 warps x 2 blocks/SM (128 regs/thread); 1 = 12 warps x 1 block/SM (168 regs/thread)
+template <int V>
+struct Shape {
+    static constexpr int WARPS = V == 0 ? 8 : 12;
+    static constexpr int BLOCKS = V == 0 ? 2 : 1;
+};
+constexpr int NUM_SHAPES = 2;
+constexpr int P_ROWS = 8, D_ROWS = 16;
+constexpr int GROUP = 4;                // rows per TMA box
+constexpr int NBAR = 2;                 // mbarriers per warp: the group being consumed + the one in flight
 
 // The mask is 1 byte per cell, and TMA wants the first byte of a box 16-byte aligned in global
 // memory: the strip origin x0 is only a multiple of 4, so the mask box starts at x0 rounded down
-// to 16 and is MBOX = 144 bytes wide; each 2-row box gets its own 128 B aligned slot.
+// to 16 and is MBOX = 144 bytes wide; each 4-row box gets its own 128 B aligned slot.
 constexpr int MBOX = SW + 16;
-constexpr int M_SLOT = 384;             // >= GROUP * MBOX, multiple of 128
-constexpr int M_SLOTS = M_ROWS / GROUP;
+constexpr int M_SLOT = 640;             // >= GROUP * MBOX, multiple of 128
+constexpr int M_SLOTS = 4;             // 16 rows: like div, a mask row is needed again for T more iterations
 static_assert(GROUP * MBOX <= M_SLOT && M_SLOT % 128 == 0, "mask slot too small");
+static_assert(P_ROWS == 2 * GROUP && D_ROWS >= JACOBI_TB_MAX_DEPTH + 2 * GROUP, "ring depths");
 
 struct __align__(128) WarpSmem {
     float p[P_ROWS][SW];
@@ -62,7 +69,7 @@ struct __align__(128) WarpSmem {
     unsigned char pad[128 - NBAR * 8];
 };
 static_assert(sizeof(WarpSmem) % 128 == 0, "per-warp shared memory must keep 128 B alignment");
-constexpr size_t SMEM_BYTES = WARPS * sizeof(WarpSmem);
+
 
 struct TBParams {
     float* pout;      // local row 0 of the output field
@@ -110,14 +117,21 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 }
 
 // shared-memory byte addresses of this lane's 16-byte column group in the three rings
-struct LaneAddr { uint32_t p, d, m; };
+// plus all-ones flags for the lane holding grid column 0 (as its column 0) / width-1 (as column 3)
+struct LaneAddr { uint32_t p, d, m, edge_l, edge_r, mkeep; };
+
+// blocked-neighbour bits (one byte per column) of input row i for this lane's 4 columns, straight
+// from the TMA-filled ring; the grid-edge L / R bits are dropped (handled through edge_l / edge_r)
+__device__ __forceinline__ uint32_t mask_of_row(const LaneAddr& sa, int i) {
+    return lds32(sa.m + (uint32_t)((i >> 2) & (M_SLOTS - 1)) * M_SLOT + (uint32_t)(i & 3) * MBOX) & sa.mkeep;
+}
 
 // One input row: advance every time level by one row.  a[t][.] holds the two newest rows of
 // level t (slot PAR = older, PAR^1 = newer); afterwards slot PAR holds the newest.
 // Column j of a lane is strip column 4*lane + j.
 template <int T, bool PZERO, int PAR, bool SLOW>
-__device__ __forceinline__ void row_step(float (&a)[T][2][4], const uint32_t (&mk)[T], const LaneAddr& sa,
-                                         int i, int lane, float (&out)[4]) {
+__device__ __forceinline__ void row_step(float (&a)[T][2][4], const LaneAddr& sa, int i, int lane,
+                                         float (&out)[4]) {
     constexpr unsigned FULL = 0xffffffffu;
     float nw[4];
     if (PZERO) {
@@ -136,8 +150,11 @@ __device__ __forceinline__ void row_step(float (&a)[T][2][4], const uint32_t (&m
         const float d[4] = {dv.x, dv.y, dv.z, dv.w};
         // left / right neighbours across lanes (lanes 0 and 31 receive wrapped garbage for the
         // strip's outermost columns, which lie in the discarded halo)
-        const float sl = __shfl_sync(FULL, mid[3], lane_l);
-        const float sr = __shfl_sync(FULL, mid[0], lane_r);
+        // at the grid's left / right edge the neighbour is the cell itself (clamp-to-edge), which
+        // is what the blocked bit would select; doing it here keeps edge strips on the fast body
+        const float sl = bitsel(mid[0], __shfl_sync(FULL, mid[3], lane_l), sa.edge_l);
+        const float sr = bitsel(mid[3], __shfl_sync(FULL, mid[0], lane_r), sa.edge_r);
+        const uint32_t mrow_bits = SLOW ? mask_of_row(sa, i - t) : 0u;
         float res[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -147,7 +164,7 @@ __device__ __forceinline__ void row_step(float (&a)[T][2][4], const uint32_t (&m
             float y1 = old[j];       // row - 1 ("B")
             float y2 = nw[j];        // row + 1 ("T")
             if (SLOW) {
-                const uint32_t bits = mk[t - 1] >> (8 * j);
+                const uint32_t bits = mrow_bits >> (8 * j);
                 x1 = (bits & NB_L) ? C : x1;
                 x2 = (bits & NB_R) ? C : x2;
                 y1 = (bits & NB_B) ? C : y1;
@@ -162,12 +179,67 @@ __device__ __forceinline__ void row_step(float (&a)[T][2][4], const uint32_t (&m
     for (int c = 0; c < 4; ++c) out[c] = nw[c];
 }
 
-template <int T, bool PZERO>
-__global__ void __launch_bounds__(WARPS * 32, 2)
+// Packed variant of row_step: the same arithmetic on Blackwell's 2-wide fp32 instructions
+// (FADD2 / FMUL2, PTX add/mul.rn.f32x2: each half is an IEEE-rounded fp32 operation, so results
+// stay bit-identical).  A lane's 4 columns are two aligned register pairs (c0,c1), (c2,c3).  The
+// horizontal sum x1 + x2 mixes columns across pairs, so it is formed by scalar adds written
+// straight into an aligned pair; the vertical neighbours, the divergence and the scale are
+// already pair-aligned: 2 + 4 instructions per 2 cells instead of 10.
+__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+
+template <int T, bool PZERO, int PAR, bool SLOW>
+__device__ __forceinline__ void row_step2(float2 (&a)[T][2][2], const LaneAddr& sa, int i, int lane,
+                                          float2 (&out)[2]) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const float2 quarter = make_float2(0.25f, 0.25f);
+    float2 nw[2];
+    if (PZERO) {
+        nw[0] = nw[1] = make_float2(0.0f, 0.0f);
+    } else {
+        const float4 v = lds128(sa.p + (uint32_t)(i & (P_ROWS - 1)) * (SW * 4));
+        nw[0] = make_float2(v.x, v.y);
+        nw[1] = make_float2(v.z, v.w);
+    }
+    const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
+#pragma unroll
+    for (int t = 1; t <= T; ++t) {
+        float2(&old)[2] = a[t - 1][PAR];
+        float2(&mid)[2] = a[t - 1][PAR ^ 1];
+        const float4 dv = lds128(sa.d + (uint32_t)((i - t) & (D_ROWS - 1)) * (SW * 4));
+        const float sl = bitsel(mid[0].x, __shfl_sync(FULL, mid[1].y, lane_l), sa.edge_l);
+        const float sr = bitsel(mid[1].y, __shfl_sync(FULL, mid[0].x, lane_r), sa.edge_r);
+        float2 s0, s1, y10 = old[0], y11 = old[1], y20 = nw[0], y21 = nw[1];
+        if (SLOW) {
+            const uint32_t m = mask_of_row(sa, i - t);
+            const float c0 = mid[0].x, c1 = mid[0].y, c2 = mid[1].x, c3 = mid[1].y;
+            s0.x = ((m & (NB_L << 0)) ? c0 : sl) + ((m & (NB_R << 0)) ? c0 : c1);
+            s0.y = ((m & (NB_L << 8)) ? c1 : c0) + ((m & (NB_R << 8)) ? c1 : c2);
+            s1.x = ((m & (NB_L << 16)) ? c2 : c1) + ((m & (NB_R << 16)) ? c2 : c3);
+            s1.y = ((m & (NB_L << 24)) ? c3 : c2) + ((m & (NB_R << 24)) ? c3 : sr);
+            y10.x = (m & (NB_B << 0)) ? c0 : y10.x;   y20.x = (m & (NB_T << 0)) ? c0 : y20.x;
+            y10.y = (m & (NB_B << 8)) ? c1 : y10.y;   y20.y = (m & (NB_T << 8)) ? c1 : y20.y;
+            y11.x = (m & (NB_B << 16)) ? c2 : y11.x;  y21.x = (m & (NB_T << 16)) ? c2 : y21.x;
+            y11.y = (m & (NB_B << 24)) ? c3 : y11.y;  y21.y = (m & (NB_T << 24)) ? c3 : y21.y;
+        } else {
+            s0 = make_float2(sl + mid[0].y, mid[0].x + mid[1].x);
+            s1 = make_float2(mid[0].y + mid[1].y, mid[1].x + sr);
+        }
+        // ((x1 + x2) + y1) + y2 - b, then * 0.25: the shader's left-to-right order
+        const float2 r0 = __fmul2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(s0, y10), y20), neg2(make_float2(dv.x, dv.y))), quarter);
+        const float2 r1 = __fmul2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(s1, y11), y21), neg2(make_float2(dv.z, dv.w))), quarter);
+        old[0] = nw[0]; old[1] = nw[1];
+        nw[0] = r0; nw[1] = r1;
+    }
+    out[0] = nw[0]; out[1] = nw[1];
+}
+
+template <int T, bool PZERO, bool PACKED, int V>
+__global__ void __launch_bounds__(Shape<V>::WARPS * 32, Shape<V>::BLOCKS)
 k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_d,
             const __grid_constant__ CUtensorMap map_m, const TBParams prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int WARPS = Shape<V>::WARPS;
     const int tile = blockIdx.x * WARPS + warp;
     if (tile >= prm.ntiles) return;                 // warps are independent: no block barrier below
     WarpSmem& S = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
@@ -178,7 +250,7 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
     const int out_hi = min(out_lo + prm.ch, prm.r1);
     const int y_first = out_lo - T;                          // first input row (local)
     const int nrows = (out_hi - out_lo) + 2 * T;
-    const int ngroups = (nrows + GROUP - 1) / GROUP;
+    const int ngroups = (nrows + GROUP - 1) / GROUP;   // extra rows of the last group are computed and dropped
 
     const uint32_t bar0 = smem_u32(&S.bar[0]);
     const uint32_t p_addr = smem_u32(&S.p[0][0]), d_addr = smem_u32(&S.d[0][0]), m_addr = smem_u32(&S.m[0][0]);
@@ -200,54 +272,80 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
         tma_load_2d(d_addr + ((GROUP * g) & (D_ROWS - 1)) * (SW * 4), &map_d, x0, row, bar);
         tma_load_2d(m_addr + (g & (M_SLOTS - 1)) * M_SLOT, &map_m, x0 & ~15, row, bar);
     };
-    if (lane == 0) {
-        for (int g = 0; g < PD && g < ngroups; ++g) issue(g);
-    }
+    if (lane == 0) issue(0);
 
-    float a[T][2][4];
-    uint32_t mk[T];
+    float a[PACKED ? 1 : T][2][4];                    // scalar state
+    float2 a2[PACKED ? T : 1][2][2];                  // packed state (two aligned pairs per row)
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-        mk[t] = 0u;
+        if constexpr (PACKED) {
+            a2[t][0][0] = a2[t][0][1] = a2[t][1][0] = a2[t][1][1] = make_float2(0.0f, 0.0f);
+        } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { a[t][0][c] = 0.0f; a[t][1][c] = 0.0f; }
+            for (int c = 0; c < 4; ++c) { a[t][0][c] = 0.0f; a[t][1][c] = 0.0f; }
+        }
     }
     uint32_t busy = 0u;                               // bit t-1: row i-t has a non-zero mask somewhere in the warp
     constexpr uint32_t BUSY_MASK = (1u << T) - 1u;
 
-    const LaneAddr sa{p_addr + 16u * lane, d_addr + 16u * lane, m_addr + (uint32_t)(x0 & 15) + 4u * lane};
     const int xa = x0 + 4 * lane;                     // this lane's first grid column
+    const uint32_t edge_l = xa == 0 ? 0xffffffffu : 0u, edge_r = xa + 4 == prm.w ? 0xffffffffu : 0u;
+    // the grid-edge L / R bits are honoured through edge_l / edge_r, so they need not make a row busy
+    const LaneAddr sa{p_addr + 16u * lane, d_addr + 16u * lane, m_addr + (uint32_t)(x0 & 15) + 4u * lane, edge_l, edge_r,
+                      0x0f0f0f0fu & ~((edge_l & (uint32_t)NB_L) | (edge_r & ((uint32_t)NB_R << 24)))};
     const bool st_ok = 4 * lane >= prm.hx && 4 * lane < SW - prm.hx && xa < prm.w;
     float* const out_col = prm.pout + xa;
 
-    auto finish_row = [&](int i, const float (&res)[4]) {
-        // shift the mask history and take in the mask bytes of input row i
-        const uint32_t mnew = lds32(sa.m + (uint32_t)((i / GROUP) & (M_SLOTS - 1)) * M_SLOT +
-                                    (uint32_t)(i % GROUP) * MBOX) & 0x0f0f0f0fu;
-#pragma unroll
-        for (int t = T - 1; t > 0; --t) mk[t] = mk[t - 1];
-        mk[0] = mnew;
-        busy = ((busy << 1) | (__any_sync(0xffffffffu, mnew != 0u) ? 1u : 0u)) & BUSY_MASK;
+    auto store_row = [&](int i, float r0, float r1, float r2, float r3) {
         const int ly = y_first + i - T;               // row of level T that just completed
         if (st_ok && ly >= out_lo && ly < out_hi)
-            stg_stream(reinterpret_cast<float4*>(out_col + (ptrdiff_t)ly * prm.w),
-                       make_float4(res[0], res[1], res[2], res[3]));
+            stg_stream(reinterpret_cast<float4*>(out_col + (ptrdiff_t)ly * prm.w), make_float4(r0, r1, r2, r3));
     };
+    auto one_row = [&](auto par, auto slow, int i) {
+        constexpr int PAR = decltype(par)::value;
+        constexpr bool SLOW = decltype(slow)::value;
+        if constexpr (PACKED) {
+            float2 r[2];
+            row_step2<T, PZERO, PAR, SLOW>(a2, sa, i, lane, r);
+            store_row(i, r[0].x, r[0].y, r[1].x, r[1].y);
+        } else {
+            float r[4];
+            row_step<T, PZERO, PAR, SLOW>(a, sa, i, lane, r);
+            store_row(i, r[0], r[1], r[2], r[3]);
+        }
+    };
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
 
+    // One TMA group (4 rows) per iteration: wait for it, put the next group in flight, consume it.
+    // The select-free body runs when no row in flight has a mask bit anywhere in the warp.
+    // No __syncwarp is needed before a ring slot is refilled: the slot's last readers are at least one
+    // group back, and every row ends in full-mask shuffles / votes that all lanes must have reached.
     for (int g = 0; g < ngroups; ++g) {
-        const uint32_t bar = bar0 + 8 * (g & (NBAR - 1));
-        const uint32_t parity = (g / NBAR) & 1;
-        while (!mbar_try_wait(bar, parity)) {}
-        float res[4];
+        while (!mbar_try_wait(bar0 + 8 * (g & (NBAR - 1)), (g / NBAR) & 1)) {}
         const int i0 = GROUP * g;
-        if (busy) row_step<T, PZERO, 0, true>(a, mk, sa, i0, lane, res);
-        else row_step<T, PZERO, 0, false>(a, mk, sa, i0, lane, res);
-        finish_row(i0, res);
-        if (busy) row_step<T, PZERO, 1, true>(a, mk, sa, i0 + 1, lane, res);
-        else row_step<T, PZERO, 1, false>(a, mk, sa, i0 + 1, lane, res);
-        finish_row(i0 + 1, res);
-        __syncwarp();
-        if (lane == 0 && g + PD < ngroups) issue(g + PD);
+        const uint32_t m0 = mask_of_row(sa, i0), m1 = mask_of_row(sa, i0 + 1);
+        const uint32_t m2 = mask_of_row(sa, i0 + 2), m3 = mask_of_row(sa, i0 + 3);
+        const uint32_t a0 = __any_sync(0xffffffffu, m0 != 0u) ? 1u : 0u, a1 = __any_sync(0xffffffffu, m1 != 0u) ? 1u : 0u;
+        const uint32_t a2_ = __any_sync(0xffffffffu, m2 != 0u) ? 1u : 0u, a3 = __any_sync(0xffffffffu, m3 != 0u) ? 1u : 0u;
+        if (lane == 0 && g + 1 < ngroups) issue(g + 1);
+        if (busy | a0 | a1 | a2_ | a3) {
+            // some row in flight (or arriving) carries mask bits: select body for the rows that need it
+            if (busy) one_row(I0{}, std::true_type{}, i0); else one_row(I0{}, std::false_type{}, i0);
+            busy = ((busy << 1) | a0) & BUSY_MASK;
+            if (busy) one_row(I1{}, std::true_type{}, i0 + 1); else one_row(I1{}, std::false_type{}, i0 + 1);
+            busy = ((busy << 1) | a1) & BUSY_MASK;
+            if (busy) one_row(I0{}, std::true_type{}, i0 + 2); else one_row(I0{}, std::false_type{}, i0 + 2);
+            busy = ((busy << 1) | a2_) & BUSY_MASK;
+            if (busy) one_row(I1{}, std::true_type{}, i0 + 3); else one_row(I1{}, std::false_type{}, i0 + 3);
+            busy = ((busy << 1) | a3) & BUSY_MASK;
+        } else {
+#pragma unroll 1
+            for (int h = 0; h < GROUP; h += 2) {
+                one_row(I0{}, std::false_type{}, i0 + h);
+                one_row(I1{}, std::false_type{}, i0 + h + 1);
+            }
+        }
     }
 }
 
@@ -265,20 +363,31 @@ struct MapEntry {
 
 using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TBParams);
 
-template <int T>
-KernelFn pick(bool pzero) { return pzero ? k_jacobi_tb<T, true> : k_jacobi_tb<T, false>; }
+template <int T, int V>
+KernelFn pick(bool pzero, bool packed) {
+    if (packed) return pzero ? k_jacobi_tb<T, true, true, V> : k_jacobi_tb<T, false, true, V>;
+    return pzero ? k_jacobi_tb<T, true, false, V> : k_jacobi_tb<T, false, false, V>;
+}
 
-KernelFn kernel_for(int depth, bool pzero) {
+template <int V>
+KernelFn kernel_for_shape(int depth, bool pzero, bool packed) {
     switch (depth) {
-    case 1: return pick<1>(pzero);
-    case 2: return pick<2>(pzero);
-    case 3: return pick<3>(pzero);
-    case 4: return pick<4>(pzero);
-    case 5: return pick<5>(pzero);
-    case 6: return pick<6>(pzero);
-    case 7: return pick<7>(pzero);
-    case 8: return pick<8>(pzero);
+    case 1: return pick<1, V>(pzero, packed);
+    case 2: return pick<2, V>(pzero, packed);
+    case 3: return pick<3, V>(pzero, packed);
+    case 4: return pick<4, V>(pzero, packed);
+    case 5: return pick<5, V>(pzero, packed);
+    case 6: return pick<6, V>(pzero, packed);
+    case 7: return pick<7, V>(pzero, packed);
+    case 8: return pick<8, V>(pzero, packed);
     default: return nullptr;
+    }
+}
+
+KernelFn kernel_for(int depth, bool pzero, bool packed, int shape) {
+    switch (shape) {
+    case 1: return kernel_for_shape<1>(depth, pzero, packed);
+    default: return kernel_for_shape<0>(depth, pzero, packed);
     }
 }
 
@@ -290,7 +399,8 @@ struct JacobiTB {
     int sm_count = 148;
     int chunk_override = 0;
     std::vector<MapEntry> maps;
-    bool attr_set[JACOBI_TB_MAX_DEPTH + 1][2] = {};
+    bool attr_set[JACOBI_TB_MAX_DEPTH + 1][2][2][NUM_SHAPES] = {};
+    int shape = 1;                // measured on B200 at 4096^2: 12 warps x 168 registers beats 2 x 8 warps x 128
 
     const CUtensorMap* map_for(const void* base, int w, size_t rows, int elem) {
         for (const MapEntry& e : maps)
@@ -333,6 +443,7 @@ JacobiTB* jacobi_tb_create() {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) tb->sm_count = n;
     }
     if (const char* e = getenv("NATRIX_TB_CHUNK")) tb->chunk_override = atoi(e);
+    if (const char* e = getenv("NATRIX_TB_SHAPE")) tb->shape = atoi(e) % NUM_SHAPES;
     return tb;
 }
 
@@ -346,7 +457,6 @@ bool jacobi_tb_supported(const Geom& g) {
 
 int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div, const uint8_t* nbmask, float* pout, Geom g,
                      int depth, int r0, int r1, bool p_is_zero, int packed, cudaStream_t st) {
-    (void)packed;
     if (!tb) return -1;
     if (depth < 1 || depth > JACOBI_TB_MAX_DEPTH) { tb->err = "depth out of range"; return -1; }
     if (!jacobi_tb_supported(g)) { tb->err = "grid width must be a multiple of 16 and >= 256"; return -1; }
@@ -363,6 +473,8 @@ int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div, const uin
     if (!mm) return -1;
     const CUtensorMap map_m = *mm;
 
+    const int warps = tb->shape == 0 ? 8 : 12;
+    const size_t smem = (size_t)warps * sizeof(WarpSmem);
     TBParams prm;
     prm.pout = pout;
     prm.w = g.w;
@@ -374,26 +486,27 @@ int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div, const uin
     const int rows = r1 - r0;
     int ch = tb->chunk_override;
     if (ch <= 0) {
-        // about one tile per resident warp (WARPS per SM), but never chunks so short that the
+        // about one tile per resident warp, but never chunks so short that the
         // 2*depth warm-up rows dominate
-        int nchunks = (tb->sm_count * WARPS) / prm.nstrips;
+        int nchunks = (tb->sm_count * warps * (tb->shape == 0 ? 2 : 1)) / prm.nstrips;
         if (nchunks < 1) nchunks = 1;
         ch = (rows + nchunks - 1) / nchunks;
         if (ch < 4 * depth) ch = 4 * depth;
     }
-    ch = (ch + 1) & ~1;
+    ch = (ch + 3) & ~3;
     prm.ch = ch;
     const int nchunks = (rows + ch - 1) / ch;
     prm.ntiles = prm.nstrips * nchunks;
-    const int blocks = (prm.ntiles + WARPS - 1) / WARPS;
+    const int blocks = (prm.ntiles + warps - 1) / warps;
 
-    KernelFn fn = kernel_for(depth, p_is_zero);
-    if (!tb->attr_set[depth][p_is_zero ? 1 : 0]) {
-        cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    KernelFn fn = kernel_for(depth, p_is_zero, packed != 0, tb->shape);
+    bool& attr_done = tb->attr_set[depth][p_is_zero ? 1 : 0][packed ? 1 : 0][tb->shape];
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { tb->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -1; }
-        tb->attr_set[depth][p_is_zero ? 1 : 0] = true;
+        attr_done = true;
     }
-    fn<<<blocks, WARPS * 32, SMEM_BYTES, st>>>(map_p, map_d, map_m, prm);
+    fn<<<blocks, warps * 32, smem, st>>>(map_p, map_d, map_m, prm);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { tb->err = std::string("k_jacobi_tb launch: ") + cudaGetErrorString(e); return -1; }
     return 1;

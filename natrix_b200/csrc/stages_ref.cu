@@ -12,11 +12,9 @@ namespace natrix {
 
 namespace {
 
-constexpr int BX = 256;   // threads per block, all along x: a warp reads 128/256 contiguous bytes
-
-__device__ __forceinline__ ptrdiff_t lin(const Geom& g, int x, int ly) {
-    return (ptrdiff_t)ly * g.w + x;
-}
+// 256 threads per block as 64 x 4 cells: a warp reads 128/256 contiguous bytes of one row, and the
+// rows above / below that the 5-point stencils need are served from L1 within the block
+constexpr int BX = 64, BY = 4, BT = BX * BY;
 
 // common.sh:9-19 GetNeighbours with clamp-to-edge on the GLOBAL domain, as local indices
 struct Nbr { ptrdiff_t l, r, b, t; };
@@ -30,59 +28,32 @@ __device__ __forceinline__ Nbr neighbours(const Geom& g, int x, int ly) {
     return n;
 }
 
-#define CELL_PROLOGUE                                  \
-    const int x = blockIdx.x * BX + threadIdx.x;       \
-    const int ly = r0 + (int)blockIdx.y;               \
-    if (x >= g.w || ly >= r1) return;                  \
+#define CELL_PROLOGUE                                        \
+    const int x = blockIdx.x * BX + threadIdx.x;             \
+    const int ly = r0 + (int)blockIdx.y * BY + threadIdx.y;  \
+    if (x >= g.w || ly >= r1) return;                        \
     const ptrdiff_t pos = lin(g, x, ly);
 
 // ref: shader.InitBoundaries.comp:14-34
-__global__ void __launch_bounds__(BX) k_init_boundaries(float2* __restrict__ vel, Geom g, int r0, int r1) {
+__global__ void __launch_bounds__(BT) k_init_boundaries(float2* __restrict__ vel, Geom g, int r0, int r1) {
     CELL_PROLOGUE
     const int gy = g.y0 + ly;
     if (x == 0 || x == g.w - 1 || gy == 0 || gy == g.hg - 1) vel[pos] = make_float2(0.0f, 0.0f);
 }
 
-// ref: shader.AdvectVelocity.comp:27-50.  FOLD folds InitBoundaries into the loads
-// (the in-place zeroing of the READ buffer is not observable after the step).
+// ref: shader.AdvectVelocity.comp:27-50 (arithmetic in common.cuh advect_cell)
 template <bool FOLD>
-__device__ __forceinline__ float2 load_vel(const float2* __restrict__ v, const Geom& g, int x, int gy) {
-    if (FOLD && (x == 0 || x == g.w - 1 || gy == 0 || gy == g.hg - 1)) return make_float2(0.0f, 0.0f);
-    return v[lin(g, x, gy - g.y0)];
-}
-
-template <bool FOLD>
-__global__ void __launch_bounds__(BX)
+__global__ void __launch_bounds__(BT)
 k_advect(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, float2* __restrict__ vout,
          Geom g, int r0, int r1, float dt, float speed, float diss, int* __restrict__ err) {
     CELL_PROLOGUE
     if (obs[pos] != OBS_FREE) { vout[pos] = make_float2(0.0f, 0.0f); return; }
     const int gy = g.y0 + ly;
-    const float2 vel = load_vel<FOLD>(vin, g, x, gy);
-    const float fx = (float)x - vel.x * dt * speed;
-    const float fy = (float)gy - vel.y * dt * speed;
-    Corners c = corners(fx, fy, g.w, g.hg);
-    // a slab can only gather from rows it holds; anything else is reported, never guessed
-    const int lo = g.y0 - g.halo, hi = g.y0 + g.hl + g.halo - 1;
-    if (c.by < lo || c.ty > hi) {
-        *err = 1;
-        c.by = clampi(c.by, lo, hi);
-        c.ty = clampi(c.ty, lo, hi);
-    }
-    const float2 lt = load_vel<FOLD>(vin, g, c.bx, c.ty);
-    const float2 rt = load_vel<FOLD>(vin, g, c.tx, c.ty);
-    const float2 lb = load_vel<FOLD>(vin, g, c.bx, c.by);
-    const float2 rb = load_vel<FOLD>(vin, g, c.tx, c.by);
-    const float h1x = mixf(lt.x, rt.x, c.dx), h1y = mixf(lt.y, rt.y, c.dx);
-    const float h2x = mixf(lb.x, rb.x, c.dx), h2y = mixf(lb.y, rb.y, c.dx);
-    float2 o;
-    o.x = clampf(mixf(h2x, h1x, c.dy) * diss, -1.0f, 1.0f);
-    o.y = clampf(mixf(h2y, h1y, c.dy) * diss, -1.0f, 1.0f);
-    vout[pos] = o;
+    vout[pos] = advect_cell<FOLD>(vin, g, x, gy, load_vel<FOLD>(vin, g, x, gy), dt, speed, diss, err);
 }
 
 // ref: shader.CalcVorticity.comp:20-26
-__global__ void __launch_bounds__(BX)
+__global__ void __launch_bounds__(BT)
 k_vorticity(const float2* __restrict__ vel, float* __restrict__ vort, Geom g, int r0, int r1) {
     CELL_PROLOGUE
     const Nbr n = neighbours(g, x, ly);
@@ -91,27 +62,18 @@ k_vorticity(const float2* __restrict__ vel, float* __restrict__ vort, Geom g, in
 }
 
 // ref: shader.ApplyVorticity.comp:26-39
-__global__ void __launch_bounds__(BX)
+__global__ void __launch_bounds__(BT)
 k_confinement(const float2* __restrict__ vin, const float* __restrict__ vort, float2* __restrict__ vout,
               Geom g, int r0, int r1, float dt, float scale) {
     CELL_PROLOGUE
     const Nbr n = neighbours(g, x, ly);
-    const float wL = vort[n.l], wR = vort[n.r], wB = vort[n.b], wT = vort[n.t], wC = vort[pos];
-    float fx = 0.5f * (fabsf(wT) - fabsf(wB));
-    float fy = 0.5f * (fabsf(wR) - fabsf(wL));
-    const float m = fmaxf(2.4414e-4f, fx * fx + fy * fy);
-    const float inv = 1.0f / sqrtf(m);
-    fx = fx * inv;
-    fy = fy * inv;
-    const float k = scale * wC;
-    fx = fx * k;
-    fy = fy * (-k);
+    const float2 f = confinement_force(vort[n.l], vort[n.r], vort[n.b], vort[n.t], vort[pos], scale, dt);
     const float2 v = vin[pos];
-    vout[pos] = make_float2(v.x + fx * dt, v.y + fy * dt);
+    vout[pos] = make_float2(v.x + f.x, v.y + f.y);
 }
 
 // ref: shader.Viscosity.comp:24-31
-__global__ void __launch_bounds__(BX)
+__global__ void __launch_bounds__(BT)
 k_viscosity(const float2* __restrict__ vin, float2* __restrict__ vout, Geom g, int r0, int r1,
             float alpha, float rbeta) {
     CELL_PROLOGUE
@@ -125,7 +87,7 @@ k_viscosity(const float2* __restrict__ vin, float2* __restrict__ vout, Geom g, i
 
 // ref: shader.Divergence.comp:22-40.  Also emits the blocked-neighbour mask (nullable) that
 // the mask-based Jacobi / gradient kernels consume.
-__global__ void __launch_bounds__(BX)
+__global__ void __launch_bounds__(BT)
 k_divergence(const float2* __restrict__ vel, const uint8_t* __restrict__ obs, float* __restrict__ div,
              uint8_t* __restrict__ nbmask, Geom g, int r0, int r1) {
     CELL_PROLOGUE
@@ -149,7 +111,7 @@ k_divergence(const float2* __restrict__ vel, const uint8_t* __restrict__ obs, fl
 }
 
 // ref: shader.Poisson.comp:24-37 (reads the obstacle map like the shader does)
-__global__ void __launch_bounds__(BX)
+__global__ void __launch_bounds__(BT)
 k_poisson_ref(const float* __restrict__ pin, const float* __restrict__ div,
               const uint8_t* __restrict__ obs, float* __restrict__ pout, Geom g, int r0, int r1) {
     CELL_PROLOGUE
@@ -163,7 +125,7 @@ k_poisson_ref(const float* __restrict__ pin, const float* __restrict__ div,
 }
 
 // same sweep driven by the blocked-neighbour mask (13 B/cell instead of 20)
-__global__ void __launch_bounds__(BX)
+__global__ void __launch_bounds__(BT)
 k_poisson_mask(const float* __restrict__ pin, const float* __restrict__ div,
                const uint8_t* __restrict__ nbmask, float* __restrict__ pout, Geom g, int r0, int r1) {
     CELL_PROLOGUE
@@ -177,7 +139,7 @@ k_poisson_mask(const float* __restrict__ pin, const float* __restrict__ div,
 }
 
 // ref: shader.SubtractGradient.comp:24-46
-__global__ void __launch_bounds__(BX)
+__global__ void __launch_bounds__(BT)
 k_gradient_ref(const float2* __restrict__ vin, const float* __restrict__ p,
                const uint8_t* __restrict__ obs, float2* __restrict__ vout, Geom g, int r0, int r1) {
     CELL_PROLOGUE
@@ -193,25 +155,9 @@ k_gradient_ref(const float2* __restrict__ vin, const float* __restrict__ p,
     vout[pos] = v;
 }
 
-__global__ void __launch_bounds__(BX)
-k_gradient_mask(const float2* __restrict__ vin, const float* __restrict__ p,
-                const uint8_t* __restrict__ nbmask, float2* __restrict__ vout, Geom g, int r0, int r1) {
-    CELL_PROLOGUE
-    const uint8_t m = nbmask[pos];
-    const float c = p[pos];
-    const float x1 = (m & NB_L) ? c : p[pos - 1];
-    const float x2 = (m & NB_R) ? c : p[pos + 1];
-    const float y1 = (m & NB_B) ? c : p[pos - g.w];
-    const float y2 = (m & NB_T) ? c : p[pos + g.w];
-    float2 v = vin[pos];
-    v.x = v.x - 0.5f * (x2 - x1);
-    v.y = v.y - 0.5f * (y2 - y1);
-    vout[pos] = v;
-}
-
 // ref: shader.AddVelocity.comp:26-35, applied b.n times in sequence per cell (each application
 // includes the all-cell clamp) - identical arithmetic to b.n separate dispatches.
-__global__ void __launch_bounds__(BX)
+__global__ void __launch_bounds__(BT)
 k_add_velocity(const float2* __restrict__ vin, float2* __restrict__ vout, Geom g, int r0, int r1,
                const __grid_constant__ SplatVBatch b) {
     CELL_PROLOGUE
@@ -233,11 +179,11 @@ k_add_velocity(const float2* __restrict__ vin, float2* __restrict__ vout, Geom g
 }
 
 // ref: shader.AddCircleObstacle.comp:24-36 (x0/y0c: offset of the launched window)
-__global__ void __launch_bounds__(BX)
+__global__ void __launch_bounds__(BT)
 k_add_circle(uint8_t* __restrict__ obs, Geom g, int x0, int xe, int r0, int r1, float sx, float sy,
              float radius) {
     const int x = x0 + blockIdx.x * BX + threadIdx.x;
-    const int ly = r0 + (int)blockIdx.y;
+    const int ly = r0 + (int)blockIdx.y * BY + threadIdx.y;
     if (x >= xe || ly >= r1) return;
     const float ex = sx - (float)x, ey = sy - (float)(g.y0 + ly);
     if (sqrtf(ex * ex + ey * ey) <= radius) obs[lin(g, x, ly)] = OBS_DYNAMIC;
@@ -247,7 +193,7 @@ k_add_circle(uint8_t* __restrict__ obs, Geom g, int x0, int xe, int r0, int r1, 
 __device__ __forceinline__ float tri_sign(float ax, float ay, float bx, float by, float cx, float cy) {
     return ((ax - cx) * (by - cy)) - ((bx - cx) * (ay - cy));
 }
-__global__ void __launch_bounds__(BX)
+__global__ void __launch_bounds__(BT)
 k_add_triangle(uint8_t* __restrict__ obs, Geom g, int r0, int r1, float p1x, float p1y, float p2x,
                float p2y, float p3x, float p3y, int is_static) {
     CELL_PROLOGUE
@@ -309,7 +255,10 @@ k_stats_final(const double* __restrict__ scratch, double* __restrict__ out4) {
     if (threadIdx.x == 0) { out4[0] = v.s; out4[1] = v.q; out4[2] = v.lo; out4[3] = v.hi; }
 }
 
-inline dim3 cell_grid(const Geom& g, int r0, int r1) { return dim3((g.w + BX - 1) / BX, r1 - r0, 1); }
+inline dim3 cell_grid(const Geom& g, int r0, int r1) {
+    return dim3((g.w + BX - 1) / BX, (r1 - r0 + BY - 1) / BY, 1);
+}
+const dim3 CELL_BLOCK(BX, BY, 1);
 
 }  // namespace
 
@@ -317,67 +266,61 @@ inline dim3 cell_grid(const Geom& g, int r0, int r1) { return dim3((g.w + BX - 1
 
 int launch_init_boundaries(float2* vel, Geom g, int r0, int r1, cudaStream_t st) {
     ROWS_OR_RETURN
-    k_init_boundaries<<<cell_grid(g, r0, r1), BX, 0, st>>>(vel, g, r0, r1);
+    k_init_boundaries<<<cell_grid(g, r0, r1), CELL_BLOCK, 0, st>>>(vel, g, r0, r1);
     return 1;
 }
 int launch_advect(const float2* vin, const uint8_t* obs, float2* vout, Geom g, int r0, int r1,
                   float dt, float speed, float diss, bool fold, int* err, cudaStream_t st) {
     ROWS_OR_RETURN
-    if (fold) k_advect<true><<<cell_grid(g, r0, r1), BX, 0, st>>>(vin, obs, vout, g, r0, r1, dt, speed, diss, err);
-    else k_advect<false><<<cell_grid(g, r0, r1), BX, 0, st>>>(vin, obs, vout, g, r0, r1, dt, speed, diss, err);
+    if (fold) k_advect<true><<<cell_grid(g, r0, r1), CELL_BLOCK, 0, st>>>(vin, obs, vout, g, r0, r1, dt, speed, diss, err);
+    else k_advect<false><<<cell_grid(g, r0, r1), CELL_BLOCK, 0, st>>>(vin, obs, vout, g, r0, r1, dt, speed, diss, err);
     return 1;
 }
 int launch_vorticity(const float2* vel, float* vort, Geom g, int r0, int r1, cudaStream_t st) {
     ROWS_OR_RETURN
-    k_vorticity<<<cell_grid(g, r0, r1), BX, 0, st>>>(vel, vort, g, r0, r1);
+    k_vorticity<<<cell_grid(g, r0, r1), CELL_BLOCK, 0, st>>>(vel, vort, g, r0, r1);
     return 1;
 }
 int launch_confinement(const float2* vin, const float* vort, float2* vout, Geom g, int r0, int r1,
                        float dt, float scale, cudaStream_t st) {
     ROWS_OR_RETURN
-    k_confinement<<<cell_grid(g, r0, r1), BX, 0, st>>>(vin, vort, vout, g, r0, r1, dt, scale);
+    k_confinement<<<cell_grid(g, r0, r1), CELL_BLOCK, 0, st>>>(vin, vort, vout, g, r0, r1, dt, scale);
     return 1;
 }
 int launch_viscosity(const float2* vin, float2* vout, Geom g, int r0, int r1, float alpha, float rbeta,
                      cudaStream_t st) {
     ROWS_OR_RETURN
-    k_viscosity<<<cell_grid(g, r0, r1), BX, 0, st>>>(vin, vout, g, r0, r1, alpha, rbeta);
+    k_viscosity<<<cell_grid(g, r0, r1), CELL_BLOCK, 0, st>>>(vin, vout, g, r0, r1, alpha, rbeta);
     return 1;
 }
 int launch_divergence(const float2* vel, const uint8_t* obs, float* div, uint8_t* nbmask, Geom g, int r0,
                       int r1, cudaStream_t st) {
     ROWS_OR_RETURN
-    k_divergence<<<cell_grid(g, r0, r1), BX, 0, st>>>(vel, obs, div, nbmask, g, r0, r1);
+    k_divergence<<<cell_grid(g, r0, r1), CELL_BLOCK, 0, st>>>(vel, obs, div, nbmask, g, r0, r1);
     return 1;
 }
 int launch_poisson_ref(const float* pin, const float* div, const uint8_t* obs, float* pout, Geom g, int r0,
                        int r1, cudaStream_t st) {
     ROWS_OR_RETURN
-    k_poisson_ref<<<cell_grid(g, r0, r1), BX, 0, st>>>(pin, div, obs, pout, g, r0, r1);
+    k_poisson_ref<<<cell_grid(g, r0, r1), CELL_BLOCK, 0, st>>>(pin, div, obs, pout, g, r0, r1);
     return 1;
 }
 int launch_poisson_mask(const float* pin, const float* div, const uint8_t* nbmask, float* pout, Geom g,
                         int r0, int r1, cudaStream_t st) {
     ROWS_OR_RETURN
-    k_poisson_mask<<<cell_grid(g, r0, r1), BX, 0, st>>>(pin, div, nbmask, pout, g, r0, r1);
+    k_poisson_mask<<<cell_grid(g, r0, r1), CELL_BLOCK, 0, st>>>(pin, div, nbmask, pout, g, r0, r1);
     return 1;
 }
 int launch_gradient_ref(const float2* vin, const float* p, const uint8_t* obs, float2* vout, Geom g, int r0,
                         int r1, cudaStream_t st) {
     ROWS_OR_RETURN
-    k_gradient_ref<<<cell_grid(g, r0, r1), BX, 0, st>>>(vin, p, obs, vout, g, r0, r1);
-    return 1;
-}
-int launch_gradient_mask(const float2* vin, const float* p, const uint8_t* nbmask, float2* vout, Geom g,
-                         int r0, int r1, cudaStream_t st) {
-    ROWS_OR_RETURN
-    k_gradient_mask<<<cell_grid(g, r0, r1), BX, 0, st>>>(vin, p, nbmask, vout, g, r0, r1);
+    k_gradient_ref<<<cell_grid(g, r0, r1), CELL_BLOCK, 0, st>>>(vin, p, obs, vout, g, r0, r1);
     return 1;
 }
 int launch_add_velocity(const float2* vin, float2* vout, Geom g, int r0, int r1, const SplatVBatch& b,
                         cudaStream_t st) {
     ROWS_OR_RETURN
-    k_add_velocity<<<cell_grid(g, r0, r1), BX, 0, st>>>(vin, vout, g, r0, r1, b);
+    k_add_velocity<<<cell_grid(g, r0, r1), CELL_BLOCK, 0, st>>>(vin, vout, g, r0, r1, b);
     return 1;
 }
 int launch_add_circle(uint8_t* obs, Geom g, int r0, int r1, float sx, float sy, float radius, bool bbox,
@@ -397,14 +340,14 @@ int launch_add_circle(uint8_t* obs, Geom g, int r0, int r1, float sx, float sy, 
         r1 = yhi < r1 - 1 ? (int)yhi + 1 : r1;
     }
     if (r1 <= r0 || xe <= x0) return 0;
-    dim3 grid((xe - x0 + BX - 1) / BX, r1 - r0, 1);
-    k_add_circle<<<grid, BX, 0, st>>>(obs, g, x0, xe, r0, r1, sx, sy, radius);
+    dim3 grid((xe - x0 + BX - 1) / BX, (r1 - r0 + BY - 1) / BY, 1);
+    k_add_circle<<<grid, CELL_BLOCK, 0, st>>>(obs, g, x0, xe, r0, r1, sx, sy, radius);
     return 1;
 }
 int launch_add_triangle(uint8_t* obs, Geom g, int r0, int r1, float p1x, float p1y, float p2x, float p2y,
                         float p3x, float p3y, int is_static, cudaStream_t st) {
     ROWS_OR_RETURN
-    k_add_triangle<<<cell_grid(g, r0, r1), BX, 0, st>>>(obs, g, r0, r1, p1x, p1y, p2x, p2y, p3x, p3y, is_static);
+    k_add_triangle<<<cell_grid(g, r0, r1), CELL_BLOCK, 0, st>>>(obs, g, r0, r1, p1x, p1y, p2x, p2y, p3x, p3y, is_static);
     return 1;
 }
 int launch_obs_expand(const uint8_t* obs, float2* out, size_t n, cudaStream_t st) {
