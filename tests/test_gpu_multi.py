@@ -1,0 +1,27 @@
+"""Multi-GPU parity (pytest -m gpu, skipped with fewer than 2 devices): torchrun over NCCL, the
+slab run must be bit-identical to the single-GPU run (scripts/slab_check.py)."""
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpus():
+    import torch
+
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_slabs_bit_identical_to_single_gpu(world):
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world), str(ROOT / "scripts" / "slab_check.py"),
+           "1024", "1024", "3", "37"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "SLAB_CHECK PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
