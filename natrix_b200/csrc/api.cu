@@ -59,6 +59,7 @@ struct natrix_sim {
     int pipeline = 1, jacobi_depth = 8, timing = 0, graph = 0, packed = 1;
     // bookkeeping
     std::vector<SplatV> pending;                 // add_velocity calls not yet applied (pipeline 1)
+    std::vector<int> heavy;                      // merged [lo, hi) local-row intervals stamped with obstacles this step
     bool obs_dirty = false, p_is_zero = false, fused_pre = false;
     int* d_err = nullptr;                        // [0] advection left the slab's halo, [1] some |v| > 1 in the READ velocity
     int* h_err = nullptr;
@@ -96,6 +97,28 @@ cudaError_t alloc_rows(T** base, T** view, const natrix_sim* s) {
     e = cudaMemsetAsync(*base, 0, s->cells_alloc * sizeof(T), s->st);
     *view = *base + (size_t)s->g.halo * s->g.w;
     return e;
+}
+
+// remember which rows carry obstacles (scheduling hint for the Jacobi kernel); keeps the list merged
+void mark_heavy_rows(natrix_sim* s, double glo, double ghi) {
+    const int margin = 2;
+    int lo = (int)std::floor(glo) - margin - s->g.y0, hi = (int)std::ceil(ghi) + margin + 1 - s->g.y0;
+    lo = std::max(lo, -s->g.halo);
+    hi = std::min(hi, s->g.hl + s->g.halo);
+    if (hi <= lo) return;
+    std::vector<int> out;
+    bool placed = false;
+    for (size_t k = 0; k + 1 < s->heavy.size(); k += 2) {
+        int a = s->heavy[k], b = s->heavy[k + 1];
+        if (b < lo) { out.push_back(a); out.push_back(b); }
+        else if (a > hi) {
+            if (!placed) { out.push_back(lo); out.push_back(hi); placed = true; }
+            out.push_back(a); out.push_back(b);
+        } else { lo = std::min(lo, a); hi = std::max(hi, b); }
+    }
+    if (!placed) { out.push_back(lo); out.push_back(hi); }
+    if (out.size() > 64) { out = {out.front(), out.back()}; }      // too fragmented: one interval
+    s->heavy.swap(out);
 }
 
 int select_device(const natrix_sim* s) {
@@ -242,7 +265,8 @@ int phase_jacobi(natrix_sim* s, int sweeps) {
         } else {
             int t = left < s->jacobi_depth ? left : s->jacobi_depth;
             int n = jacobi_tb_launch(s->tb, s->p[s->pr], s->div, s->nbm, s->p[1 - s->pr], g, t,
-                                     s->ext_lo(left - t), s->ext_hi(left - t), s->p_is_zero, s->packed, s->st);
+                                     s->ext_lo(left - t), s->ext_hi(left - t), s->p_is_zero, s->packed,
+                                     s->heavy.data(), (int)s->heavy.size() / 2, s->st);
             if (n < 0) return fail(NATRIX_ERR_CUDA, std::string("jacobi_tb: ") + jacobi_tb_error(s->tb));
             s->launches += n;
             s->pr = 1 - s->pr;
@@ -271,6 +295,7 @@ int phase_project(natrix_sim* s) {
         s->launches += 1;
         s->obs_dirty = false;
     }
+    s->heavy.clear();
     stamp(s, ST_COUNT);
     CU(cudaGetLastError());
     return 0;
@@ -431,6 +456,7 @@ int natrix_add_circle_obstacle(natrix_sim* s, float px, float py, float radius, 
     const Geom& g = s->g;
     s->launches += launch_add_circle(s->obs, g, s->ext_lo(g.halo), s->ext_hi(g.halo), px * (float)g.w,
                                      py * (float)g.hg, radius, s->pipeline != 0, s->st);
+    if (radius >= 0.0f) mark_heavy_rows(s, (double)py * g.hg - radius, (double)py * g.hg + radius);
     s->obs_dirty = true;
     CU(cudaGetLastError());
     return 0;
@@ -443,6 +469,12 @@ int natrix_add_triangle_obstacle(natrix_sim* s, float p1x, float p1y, float p2x,
     const Geom& g = s->g;
     s->launches += launch_add_triangle(s->obs, g, s->ext_lo(g.halo), s->ext_hi(g.halo), p1x, p1y, p2x, p2y,
                                        p3x, p3y, is_static, s->st);
+    {
+        const double ys[3] = {(double)p1y * g.hg, (double)p2y * g.hg, (double)p3y * g.hg};
+        const double ymin = std::min(ys[0], std::min(ys[1], ys[2])), ymax = std::max(ys[0], std::max(ys[1], ys[2]));
+        // a degenerate triangle selects whole lines of cells (see stages_ref.cu): call every row heavy
+        if (ymax - ymin < 1.0) mark_heavy_rows(s, 0.0, (double)g.hg); else mark_heavy_rows(s, ymin, ymax);
+    }
     s->obs_dirty = true;
     CU(cudaGetLastError());
     return 0;
@@ -566,6 +598,7 @@ int natrix_copy_in(natrix_sim* s, int field, const void* host, size_t bytes) {
         if (!s->d_tmp2) CU(cudaMalloc((void**)&s->d_tmp2, n * sizeof(float2)));
         CU(cudaMemcpyAsync(s->d_tmp2, host, bytes, cudaMemcpyHostToDevice, s->st));
         s->launches += launch_obs_pack(s->d_tmp2, s->obs, n, s->st);
+        mark_heavy_rows(s, 0.0, (double)s->g.hg);
         s->obs_dirty = true;
         CU(cudaStreamSynchronize(s->st));
         return 0;
