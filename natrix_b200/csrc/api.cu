@@ -200,9 +200,11 @@ int phase_advect(natrix_sim* s, float dt) {
     if (s->fused_pre) {
         // advect + vorticity + confinement + [viscosity] + divergence + mask in one pass; the
         // velocity buffer flips once (the intermediate velocities never reach memory)
+        if (s->has_borders)
+            s->launches += launch_zero_borders(s->vel[s->vr], g, s->ext_lo(g.halo), s->ext_hi(g.halo), s->st);
         s->launches += launch_preproject(s->vel[s->vr], s->obs, s->vel[1 - s->vr], s->vort, s->div, s->nbm, g, 0, g.hl,
                                          dt, s->speed, s->dissipation, s->vorticity, s->viscous != 0, s->alpha,
-                                         s->rbeta, fold, s->sm_count, s->d_err, s->st);
+                                         s->rbeta, s->sm_count, s->d_err, s->st);
         s->vr = 1 - s->vr;
         CU(cudaGetLastError());
         return 0;

@@ -41,7 +41,36 @@ __device__ __forceinline__ void copy4(float (&d)[4], const float (&s)[4]) {
     for (int j = 0; j < 4; ++j) d[j] = s[j];
 }
 
-template <bool VISCOUS, bool FOLD>
+// Bilinear back-trace of one cell (ref: shader.AdvectVelocity.comp:36-49; same expressions as
+// common.cuh advect_cell) with the two gathered rows addressed through row pointers.  SLAB adds the
+// check that the gathered rows are rows this slab holds.
+template <bool SLAB>
+__device__ __forceinline__ float2 advect_gather(const float2* __restrict__ vin, const Geom& g, int x, int gy, float2 vel,
+                                                float dt, float speed, float diss, int* __restrict__ err) {
+    const float fx = (float)x - vel.x * dt * speed;
+    const float fy = (float)gy - vel.y * dt * speed;
+    Corners c = corners(fx, fy, g.w, g.hg);
+    if (SLAB) {
+        const int lo = g.y0 - g.halo, hi = g.y0 + g.hl + g.halo - 1;
+        if (c.by < lo || c.ty > hi) *err = 1;
+        c.by = clampi(c.by, lo, hi);
+        c.ty = clampi(c.ty, lo, hi);
+    }
+    const float2* rb_ = vin + (ptrdiff_t)(c.by - g.y0) * g.w;
+    const float2* rt_ = rb_ + (c.ty - c.by) * g.w;
+    const float2 lt = rt_[c.bx], rt = rt_[c.tx], lb = rb_[c.bx], rb = rb_[c.tx];
+    const float h1x = mixf(lt.x, rt.x, c.dx), h1y = mixf(lt.y, rt.y, c.dx);
+    const float h2x = mixf(lb.x, rb.x, c.dx), h2y = mixf(lb.y, rb.y, c.dx);
+    float2 o;
+    o.x = clampf(mixf(h2x, h1x, c.dy) * diss, -1.0f, 1.0f);
+    o.y = clampf(mixf(h2y, h1y, c.dy) * diss, -1.0f, 1.0f);
+    return o;
+}
+
+// InitBoundaries (shader.InitBoundaries.comp:14-34) is NOT folded in here: when has_borders is set the
+// border lines of the READ buffer are zeroed in place by k_zero_borders first, exactly like the
+// reference's dispatch does (2 (W + H) cells; cheaper than testing every gathered corner).
+template <bool VISCOUS, bool SLAB>
 __global__ void __launch_bounds__(PWARPS * 32, 2)
 k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, float2* __restrict__ vout,
              float* __restrict__ vort, float* __restrict__ div, uint8_t* __restrict__ nbmask, const Geom g,
@@ -72,7 +101,8 @@ k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, fl
 
     for (int ly = out_lo - DEPTH; ly < out_hi + DEPTH; ++ly) {
         const int gy = g.y0 + ly;
-        // ---- stage 0: advect row ly (ref: shader.AdvectVelocity.comp:27-50, borders folded in)
+        // ---- stage 0: advect row ly (ref: shader.AdvectVelocity.comp:27-50).  All 4 cells are traced
+        // without branching (16 independent gathers in flight); solid cells are zeroed afterwards.
         float2 An[4];
         if (gy >= 0 && gy < g.hg) {
             const ptrdiff_t base = lin(g, xc0, ly);
@@ -82,16 +112,10 @@ k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, fl
             const float2 cv[4] = {make_float2(c01.x, c01.y), make_float2(c01.z, c01.w), make_float2(c23.x, c23.y),
                                   make_float2(c23.z, c23.w)};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int x = xc0 + j;
-                if ((ow >> (8 * j)) & 0xffu) {
-                    An[j] = make_float2(0.0f, 0.0f);
-                } else {
-                    float2 v = cv[j];
-                    if (FOLD && (x == 0 || x == g.w - 1 || gy == 0 || gy == g.hg - 1)) v = make_float2(0.0f, 0.0f);
-                    An[j] = advect_cell<FOLD>(vin, g, x, gy, v, prm.dt, prm.speed, prm.diss, err);
-                }
-            }
+            for (int j = 0; j < 4; ++j) An[j] = advect_gather<SLAB>(vin, g, xc0 + j, gy, cv[j], prm.dt, prm.speed, prm.diss, err);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if ((ow >> (8 * j)) & 0xffu) An[j] = make_float2(0.0f, 0.0f);
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) An[j] = make_float2(0.0f, 0.0f);
@@ -266,10 +290,9 @@ k_clamp_outside_boxes(float2* __restrict__ vel, const Geom g, int r0, int r1, co
         bool skip = false;
         for (int k = 0; k < b.n; ++k) skip = skip || in_box(b.b[k], x, g.y0 + ly);
         if (skip) continue;
-        float2 v = vel[lin(g, x, ly)];
-        v.x = clampf(v.x, -1.0f, 1.0f);
-        v.y = clampf(v.y, -1.0f, 1.0f);
-        vel[lin(g, x, ly)] = v;
+        const float2 v = vel[lin(g, x, ly)];
+        const float2 c = make_float2(clampf(v.x, -1.0f, 1.0f), clampf(v.y, -1.0f, 1.0f));
+        if (c.x != v.x || c.y != v.y) vel[lin(g, x, ly)] = c;        // rare: most cells are already in range
     }
 }
 
@@ -321,6 +344,26 @@ dim3 boxes_grid(const Boxes& b) {
     return dim3((mw + SBX - 1) / SBX, (mh + SBY - 1) / SBY, b.n);
 }
 
+// ---------------------------------------------------------------------------------------------- borders
+// ref: shader.InitBoundaries.comp:14-34 - zero the four border lines of the READ velocity in place.
+// One thread per border cell of rows [r0, r1): the two side columns, plus the first / last grid row.
+__global__ void __launch_bounds__(256)
+k_zero_borders(float2* __restrict__ vel, const Geom g, int r0, int r1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nrows = r1 - r0;
+    const float2 z = make_float2(0.0f, 0.0f);
+    if (i < nrows) {
+        vel[lin(g, 0, r0 + i)] = z;
+        vel[lin(g, g.w - 1, r0 + i)] = z;
+    } else if (i < nrows + g.w) {
+        const int top = -g.y0;                       // local row of grid row 0
+        if (top >= r0 && top < r1) vel[lin(g, i - nrows, top)] = z;
+    } else if (i < nrows + 2 * g.w) {
+        const int bot = g.hg - 1 - g.y0;
+        if (bot >= r0 && bot < r1) vel[lin(g, i - nrows - g.w, bot)] = z;
+    }
+}
+
 // ------------------------------------------------------------------------------------------- gradient
 // ref: shader.SubtractGradient.comp:24-46 via the blocked-neighbour mask; also records whether any
 // |v| > 1 leaves the step (lets the next add_velocity skip its all-cell clamp pass).
@@ -345,13 +388,67 @@ k_gradient_mask(const float2* __restrict__ vin, const float* __restrict__ p, con
     if (fabsf(v.x) > 1.0f || fabsf(v.y) > 1.0f) *over1 = 1;
 }
 
+// Same, 4 cells per thread (width % 4 == 0): three float4 pressure loads (row, row-1, row+1 - every
+// address is independent of the mask, so all loads are in flight at once), two float4 velocity loads,
+// one mask word; the columns left / right of the group come from the neighbouring lanes.
+constexpr int G4X = 32, G4Y = 8;
+__global__ void __launch_bounds__(G4X * G4Y)
+k_gradient_mask4(const float2* __restrict__ vin, const float* __restrict__ p, const uint8_t* __restrict__ nbmask,
+                 float2* __restrict__ vout, const Geom g, int r0, int r1, int* __restrict__ over1) {
+    const int x = (blockIdx.x * G4X + threadIdx.x) * 4;
+    const int ly = r0 + (int)blockIdx.y * G4Y + threadIdx.y;
+    const bool live = x < g.w && ly < r1;
+    const int xs = live ? x : 0, ys = live ? ly : r0;                 // dead threads still take part in the shuffles
+    const int gy = g.y0 + ys;
+    const ptrdiff_t pos = lin(g, xs, ys);
+    const ptrdiff_t up = lin(g, xs, max(gy - 1, 0) - g.y0), dn = lin(g, xs, min(gy + 1, g.hg - 1) - g.y0);
+    const float4 pc = *reinterpret_cast<const float4*>(p + pos);
+    const float4 pb = *reinterpret_cast<const float4*>(p + up);       // row - 1 ("B")
+    const float4 pt = *reinterpret_cast<const float4*>(p + dn);       // row + 1 ("T")
+    const uint32_t mw = *reinterpret_cast<const uint32_t*>(nbmask + pos);
+    const float4 v01 = *reinterpret_cast<const float4*>(vin + pos);
+    const float4 v23 = *reinterpret_cast<const float4*>(vin + pos + 2);
+    float pl = __shfl_up_sync(0xffffffffu, pc.w, 1), pr = __shfl_down_sync(0xffffffffu, pc.x, 1);
+    if (threadIdx.x == 0) pl = p[pos - (xs > 0 ? 1 : 0)];             // group at the start of the warp's span
+    if (threadIdx.x == G4X - 1) pr = p[pos + (xs + 4 < g.w ? 4 : 3)];
+    if (!live) return;
+    const float c[4] = {pc.x, pc.y, pc.z, pc.w};
+    const float b[4] = {pb.x, pb.y, pb.z, pb.w};
+    const float t[4] = {pt.x, pt.y, pt.z, pt.w};
+    const float vx[4] = {v01.x, v01.z, v23.x, v23.z}, vy[4] = {v01.y, v01.w, v23.y, v23.w};
+    float ox[4], oy[4];
+    bool over = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t m = mw >> (8 * j);
+        const float x1 = (m & NB_L) ? c[j] : (j > 0 ? c[j - 1] : pl);
+        const float x2 = (m & NB_R) ? c[j] : (j < 3 ? c[j + 1] : pr);
+        const float y1 = (m & NB_B) ? c[j] : b[j];
+        const float y2 = (m & NB_T) ? c[j] : t[j];
+        ox[j] = vx[j] - 0.5f * (x2 - x1);
+        oy[j] = vy[j] - 0.5f * (y2 - y1);
+        over = over || fabsf(ox[j]) > 1.0f || fabsf(oy[j]) > 1.0f;
+    }
+    float4* dst = reinterpret_cast<float4*>(vout + pos);
+    stg_stream(dst, make_float4(ox[0], oy[0], ox[1], oy[1]));
+    stg_stream(dst + 1, make_float4(ox[2], oy[2], ox[3], oy[3]));
+    if (over) *over1 = 1;
+}
+
 }  // namespace
 
 bool preproject_supported(const Geom& g) { return g.w % 4 == 0 && g.w >= 8; }
 
+int launch_zero_borders(float2* vel, Geom g, int r0, int r1, cudaStream_t st) {
+    if (r1 <= r0) return 0;
+    const int n = (r1 - r0) + 2 * g.w;
+    k_zero_borders<<<(n + 255) / 256, 256, 0, st>>>(vel, g, r0, r1);
+    return 1;
+}
+
 int launch_preproject(const float2* vin, const uint8_t* obs, float2* vout, float* vort, float* div, uint8_t* nbmask,
                       Geom g, int r0, int r1, float dt, float speed, float diss, float scale, bool viscous, float alpha,
-                      float rbeta, bool fold, int sm_count, int* err, cudaStream_t st) {
+                      float rbeta, int sm_count, int* err, cudaStream_t st) {
     if (r1 <= r0) return 0;
     PreParams prm;
     prm.r0 = r0; prm.r1 = r1;
@@ -366,11 +463,12 @@ int launch_preproject(const float2* vin, const uint8_t* obs, float2* vout, float
     nchunks = (rows + ch - 1) / ch;
     prm.ntiles = prm.nstrips * nchunks;
     const int blocks = (prm.ntiles + PWARPS - 1) / PWARPS;
+    const bool slab = g.hl != g.hg;
     if (viscous) {
-        if (fold) k_preproject<true, true><<<blocks, PWARPS * 32, 0, st>>>(vin, obs, vout, vort, div, nbmask, g, prm, err);
+        if (slab) k_preproject<true, true><<<blocks, PWARPS * 32, 0, st>>>(vin, obs, vout, vort, div, nbmask, g, prm, err);
         else k_preproject<true, false><<<blocks, PWARPS * 32, 0, st>>>(vin, obs, vout, vort, div, nbmask, g, prm, err);
     } else {
-        if (fold) k_preproject<false, true><<<blocks, PWARPS * 32, 0, st>>>(vin, obs, vout, vort, div, nbmask, g, prm, err);
+        if (slab) k_preproject<false, true><<<blocks, PWARPS * 32, 0, st>>>(vin, obs, vout, vort, div, nbmask, g, prm, err);
         else k_preproject<false, false><<<blocks, PWARPS * 32, 0, st>>>(vin, obs, vout, vort, div, nbmask, g, prm, err);
     }
     return 1;
@@ -379,8 +477,13 @@ int launch_preproject(const float2* vin, const uint8_t* obs, float2* vout, float
 int launch_gradient_mask(const float2* vin, const float* p, const uint8_t* nbmask, float2* vout, Geom g, int r0, int r1,
                          int* over1, cudaStream_t st) {
     if (r1 <= r0) return 0;
-    dim3 grid((g.w + GBX - 1) / GBX, (r1 - r0 + GBY - 1) / GBY, 1);
-    k_gradient_mask<<<grid, dim3(GBX, GBY, 1), 0, st>>>(vin, p, nbmask, vout, g, r0, r1, over1);
+    if (g.w % 4 == 0) {
+        dim3 grid((g.w / 4 + G4X - 1) / G4X, (r1 - r0 + G4Y - 1) / G4Y, 1);
+        k_gradient_mask4<<<grid, dim3(G4X, G4Y, 1), 0, st>>>(vin, p, nbmask, vout, g, r0, r1, over1);
+    } else {
+        dim3 grid((g.w + GBX - 1) / GBX, (r1 - r0 + GBY - 1) / GBY, 1);
+        k_gradient_mask<<<grid, dim3(GBX, GBY, 1), 0, st>>>(vin, p, nbmask, vout, g, r0, r1, over1);
+    }
     return 1;
 }
 

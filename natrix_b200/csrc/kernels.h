@@ -52,11 +52,13 @@ int launch_poisson_mask(const float* pin, const float* div, const uint8_t* nbmas
 // over1: device int set to non-zero when some |v| > 1 leaves the kernel (see fused.cu)
 int launch_gradient_mask(const float2* vin, const float* p, const uint8_t* nbmask, float2* vout,
                          Geom g, int r0, int r1, int* over1, cudaStream_t st);
-// fused [borders] + advect + vorticity + confinement + [viscosity] + divergence + mask, rows [r0, r1)
+// fused advect + vorticity + confinement + [viscosity] + divergence + mask, rows [r0, r1)
 bool preproject_supported(const Geom& g);
 int launch_preproject(const float2* vin, const uint8_t* obs, float2* vout, float* vort, float* div,
                       uint8_t* nbmask, Geom g, int r0, int r1, float dt, float speed, float diss, float scale,
-                      bool viscous, float alpha, float rbeta, bool fold, int sm_count, int* err, cudaStream_t st);
+                      bool viscous, float alpha, float rbeta, int sm_count, int* err, cudaStream_t st);
+// InitBoundaries restricted to the border cells of rows [r0, r1), in place
+int launch_zero_borders(float2* vel, Geom g, int r0, int r1, cudaStream_t st);
 // in-place impulses restricted to the splats' bounding boxes (n <= MAX_SPLATS)
 int launch_splat_velocity_boxes(float2* vel, Geom g, int r0, int r1, const SplatV* splats, int n,
                                 const int* over1, int sm_count, cudaStream_t st);
