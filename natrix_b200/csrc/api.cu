@@ -84,6 +84,7 @@ struct natrix_dye {
     natrix_sim* sim = nullptr;
     int w = 0, h = 0;
     float* d[2] = {nullptr, nullptr};
+    float* tables = nullptr;                    // normalised x (w floats) then y (h floats) coordinates
     int rd = 0;
     std::vector<SplatD> pending;
 };
@@ -648,6 +649,11 @@ int natrix_dye_create(natrix_sim* s, int width, int height, natrix_dye** out) {
             return fail(NATRIX_ERR_CUDA, std::string("natrix_dye_create: ") + cudaGetErrorString(e));
         }
     }
+    if (cudaMalloc((void**)&d->tables, (size_t)(width + height) * sizeof(float)) != cudaSuccess) {
+        cudaFree(d->d[0]); cudaFree(d->d[1]); delete d;
+        return fail(NATRIX_ERR_CUDA, "natrix_dye_create: out of memory");
+    }
+    s->launches += launch_dye_tables(d->tables, d->tables + width, width, height, s->g.w, s->g.hg, s->st);
     s->dyes.push_back(d);
     *out = d;
     return 0;
@@ -661,7 +667,7 @@ int natrix_dye_destroy(natrix_dye* d) {
         auto& v = d->sim->dyes;
         for (size_t i = 0; i < v.size(); ++i) if (v[i] == d) { v.erase(v.begin() + i); break; }
     }
-    cudaFree(d->d[0]); cudaFree(d->d[1]);
+    cudaFree(d->d[0]); cudaFree(d->d[1]); cudaFree(d->tables);
     delete d;
     return 0;
 }
@@ -685,8 +691,12 @@ int natrix_dye_step(natrix_dye* d, float dt, float speed, float dissipation) {
     if (int rc = select_device(s)) return rc;
     if (int rc = flush_splats(s)) return rc;     // the advect reads the CURRENT velocity
     if (int rc = flush_dye(d)) return rc;
-    s->launches += launch_dye_advect(d->d[d->rd], d->d[1 - d->rd], d->w, d->h, s->vel[s->vr], s->obs, s->g.w,
-                                     s->g.hg, dt, speed, dissipation, s->st);
+    if (s->pipeline != 0 && d->w % 4 == 0)
+        s->launches += launch_dye_advect4(d->d[d->rd], d->d[1 - d->rd], d->w, d->h, s->vel[s->vr], s->obs, s->g.w,
+                                          s->g.hg, d->tables, d->tables + d->w, dt, speed, dissipation, s->st);
+    else
+        s->launches += launch_dye_advect(d->d[d->rd], d->d[1 - d->rd], d->w, d->h, s->vel[s->vr], s->obs, s->g.w,
+                                         s->g.hg, dt, speed, dissipation, s->st);
     d->rd = 1 - d->rd;
     CU(cudaGetLastError());
     return 0;

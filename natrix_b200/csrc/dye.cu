@@ -57,6 +57,55 @@ k_dye_advect(const float* __restrict__ din, float* __restrict__ dout, int pw, in
     dout[pos] = mixf(g2, g1, q.dy) * diss;
 }
 
+// Same arithmetic, 4 dye cells of one row per thread.  The row-only half of the velocity sample
+// (normalised y, its clamped floor / ceil rows and weight, the obstacle row) is computed once per
+// thread, and the normalised coordinates come from tables filled by k_dye_tables with the exact
+// expression of the shader, so no per-cell IEEE division is left.
+constexpr int D4X = 32, D4Y = 8;
+__global__ void k_dye_tables(float* __restrict__ nx, float* __restrict__ ny, int pw, int ph, int vw, int vh) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pw) nx[i] = ((float)i / (float)pw) * (float)vw;        // fNormalisedPos.x (:46)
+    if (i < ph) ny[i] = ((float)i / (float)ph) * (float)vh;
+}
+
+__global__ void __launch_bounds__(D4X * D4Y)
+k_dye_advect4(const float* __restrict__ din, float* __restrict__ dout, int pw, int ph, const float2* __restrict__ vel,
+              const uint8_t* __restrict__ obs, int vw, int vh, const float* __restrict__ nxt,
+              const float* __restrict__ nyt, float rx, float ry, float dt, float speed, float diss) {
+    const int x0 = (blockIdx.x * D4X + threadIdx.x) * 4;
+    const int y = blockIdx.y * D4Y + threadIdx.y;
+    if (x0 >= pw || y >= ph) return;
+    const float ny = nyt[y];
+    const float my = (float)(vh - 1), mx = (float)(vw - 1);
+    const int vty = (int)clampf(ceilf(ny), 0.0f, my), vby = (int)clampf(floorf(ny), 0.0f, my);
+    const float vdy = ny - (float)vby;
+    const float2* vrow_t = vel + (size_t)vty * vw;
+    const float2* vrow_b = vel + (size_t)vby * vw;
+    const uint8_t* orow = obs + (size_t)(unsigned)ny * vw;
+    const float4 nx4 = *reinterpret_cast<const float4*>(nxt + x0);       // pw % 4 == 0
+    const float nxs[4] = {nx4.x, nx4.y, nx4.z, nx4.w};
+    float out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float nx = nxs[j];
+        const int vtx = (int)clampf(ceilf(nx), 0.0f, mx), vbx = (int)clampf(floorf(nx), 0.0f, mx);
+        const float vdx = nx - (float)vbx;
+        const float2 lt = vrow_t[vbx], rt = vrow_t[vtx], lb = vrow_b[vbx], rb = vrow_b[vtx];
+        const float vx = mixf(mixf(lb.x, rb.x, vdx), mixf(lt.x, rt.x, vdx), vdy) * rx;
+        const float vy = mixf(mixf(lb.y, rb.y, vdx), mixf(lt.y, rt.y, vdx), vdy) * ry;
+        const float fx = (float)(x0 + j) - vx * dt * speed;
+        const float fy = (float)y - vy * dt * speed;
+        const Corners q = corners(fx, fy, pw, ph);
+        const float* drow_t = din + (size_t)q.ty * pw;
+        const float* drow_b = din + (size_t)q.by * pw;
+        const float g1 = mixf(drow_t[q.bx], drow_t[q.tx], q.dx);
+        const float g2 = mixf(drow_b[q.bx], drow_b[q.tx], q.dx);
+        const float r = mixf(g2, g1, q.dy) * diss;
+        out[j] = orow[(unsigned)nx] != OBS_FREE ? 0.0f : r;
+    }
+    stg_stream(reinterpret_cast<float4*>(dout + (size_t)y * pw + x0), make_float4(out[0], out[1], out[2], out[3]));
+}
+
 }  // namespace
 
 int launch_dye_add(const float* din, float* dout, int pw, int ph, const SplatDBatch& b, cudaStream_t st) {
@@ -68,6 +117,19 @@ int launch_dye_advect(const float* din, float* dout, int pw, int ph, const float
                       int vw, int vh, float dt, float speed, float diss, cudaStream_t st) {
     dim3 grid((pw + BX - 1) / BX, (ph + BY - 1) / BY, 1);
     k_dye_advect<<<grid, dim3(BX, BY, 1), 0, st>>>(din, dout, pw, ph, vel, obs, vw, vh, dt, speed, diss);
+    return 1;
+}
+int launch_dye_tables(float* nx, float* ny, int pw, int ph, int vw, int vh, cudaStream_t st) {
+    const int n = pw > ph ? pw : ph;
+    k_dye_tables<<<(n + 255) / 256, 256, 0, st>>>(nx, ny, pw, ph, vw, vh);
+    return 1;
+}
+int launch_dye_advect4(const float* din, float* dout, int pw, int ph, const float2* vel, const uint8_t* obs, int vw,
+                       int vh, const float* nx, const float* ny, float dt, float speed, float diss, cudaStream_t st) {
+    // _ParticleSize / _VelocitySize (:34): IEEE single division, same on host and device
+    const float rx = (float)pw / (float)vw, ry = (float)ph / (float)vh;
+    dim3 grid((pw / 4 + D4X - 1) / D4X, (ph + D4Y - 1) / D4Y, 1);
+    k_dye_advect4<<<grid, dim3(D4X, D4Y, 1), 0, st>>>(din, dout, pw, ph, vel, obs, vw, vh, nx, ny, rx, ry, dt, speed, diss);
     return 1;
 }
 
