@@ -61,7 +61,9 @@ struct natrix_sim {
     std::vector<SplatV> pending;                 // add_velocity calls not yet applied (pipeline 1)
     std::vector<int> heavy;                      // merged [lo, hi) local-row intervals stamped with obstacles this step
     bool obs_dirty = false, p_is_zero = false, fused_pre = false;
-    int* d_err = nullptr;                        // [0] advection left the slab's halo, [1] some |v| > 1 in the READ velocity
+    int* d_err = nullptr;                        // [0] advection left the slab's halo; [1..] per band of OVER_BAND
+                                                 // rows: some |v| > 1 in the READ velocity
+    int nbands = 0;
     int* h_err = nullptr;
     int sm_count = 148;
     double *d_scratch = nullptr, *d_out4 = nullptr, *h_out4 = nullptr;
@@ -149,7 +151,7 @@ int flush_splats(natrix_sim* s) {
             const int n = (int)std::min<size_t>(MAX_SPLATS, s->pending.size() - i);
             s->launches += launch_splat_velocity_boxes(s->vel[s->vr], s->g, lo, hi, &s->pending[i], n, s->d_err + 1,
                                                        s->sm_count, s->st);
-            CU(cudaMemsetAsync(s->d_err + 1, 0, sizeof(int), s->st));      // every |v| <= 1 now
+            CU(cudaMemsetAsync(s->d_err + 1, 0, s->nbands * sizeof(int), s->st));      // every |v| <= 1 now
             i += n;
         }
     }
@@ -224,8 +226,12 @@ int phase_forces(natrix_sim* s, float dt) {
     stamp(s, ST_VORT);
     if (s->fused_pre) {
         stamp(s, ST_DIV);
-        CU(cudaMemsetAsync(s->p_base[s->pr], 0, s->cells_alloc * sizeof(float), s->st));
-        s->launches += 1;
+        // clear pressure (fluid_simulator.py:236-248): the first temporally blocked launch treats p as
+        // zero without reading it, so the fill itself is only needed for the 1-sweep fallback kernel
+        if (!jacobi_tb_supported(g)) {
+            CU(cudaMemsetAsync(s->p_base[s->pr], 0, s->cells_alloc * sizeof(float), s->st));
+            s->launches += 1;
+        }
         s->p_is_zero = true;
         return 0;
     }
@@ -293,11 +299,18 @@ int phase_project(natrix_sim* s) {
     stamp(s, ST_CLEAR);
     // clear obstacles (fluid_simulator.py:268-280); skipped when nothing was stamped since the
     // last clear (the map is already all zero)
-    if (s->obs_dirty || s->pipeline == 0) {
+    if (s->pipeline == 0) {
         CU(cudaMemsetAsync(s->obs_base, 0, s->cells_alloc, s->st));
         s->launches += 1;
-        s->obs_dirty = false;
+    } else if (s->obs_dirty) {
+        // only the rows that were stamped since the last clear can be non-zero
+        for (size_t k = 0; k + 1 < s->heavy.size(); k += 2) {
+            const int lo = s->heavy[k], hi = s->heavy[k + 1];
+            CU(cudaMemsetAsync(s->obs + (ptrdiff_t)lo * g.w, 0, (size_t)(hi - lo) * g.w, s->st));
+            s->launches += 1;
+        }
     }
+    s->obs_dirty = false;
     s->heavy.clear();
     stamp(s, ST_COUNT);
     CU(cudaGetLastError());
@@ -349,8 +362,9 @@ int natrix_create_slab(int width, int global_height, int row0, int rows, int hal
     if (e == cudaSuccess) e = alloc_rows(&s->vort_base, &s->vort, s);
     if (e == cudaSuccess) e = alloc_rows(&s->obs_base, &s->obs, s);
     if (e == cudaSuccess) e = alloc_rows(&s->nbm_base, &s->nbm, s);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_err, 2 * sizeof(int));
-    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_err, 0, 2 * sizeof(int), s->st);
+    s->nbands = (int)((s->rows_alloc + OVER_BAND - 1) / OVER_BAND);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_err, (1 + s->nbands) * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_err, 0, (1 + s->nbands) * sizeof(int), s->st);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_err, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_scratch, 4 * 1024 * sizeof(double));
@@ -416,7 +430,7 @@ int natrix_set_option(natrix_sim* s, int option, int value) {
         NEED(value == 0 || value == 1, "pipeline must be 0 or 1");
         if (int rc = select_device(s)) return rc;
         if (int rc = flush_splats(s)) return rc;
-        CU(cudaMemsetAsync(s->d_err + 1, 1, sizeof(int), s->st));   // pipeline 0 does not track |v| > 1
+        CU(cudaMemsetAsync(s->d_err + 1, 1, s->nbands * sizeof(int), s->st));   // pipeline 0 does not track |v| > 1
         s->pipeline = value; return 0;
     case NATRIX_OPT_JACOBI_DEPTH:
         NEED(value >= 1 && value <= JACOBI_TB_MAX_DEPTH, "jacobi depth out of range");
@@ -610,7 +624,7 @@ int natrix_copy_in(natrix_sim* s, int field, const void* host, size_t bytes) {
     CU(cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, s->st));
     CU(cudaStreamSynchronize(s->st));
     if (field == NATRIX_PRESSURE) s->p_is_zero = false;
-    if (field == NATRIX_VELOCITY) CU(cudaMemsetAsync(s->d_err + 1, 1, sizeof(int), s->st));   // unknown range
+    if (field == NATRIX_VELOCITY) CU(cudaMemsetAsync(s->d_err + 1, 1, s->nbands * sizeof(int), s->st));   // unknown range
     return 0;
 }
 

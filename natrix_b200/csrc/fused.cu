@@ -278,15 +278,17 @@ k_splat_velocity_boxes(float2* __restrict__ vel, const Geom g, const __grid_cons
 }
 
 // The clamp that every AddVelocity dispatch applies to ALL cells, for the cells outside
-// every box.  It only has work to do if some |v| > 1, which the kernel that produced the field
-// recorded in *over1; otherwise every block leaves at once.
+// every box.  It only has work to do where some |v| > 1, which the kernel that produced the field
+// recorded per band of OVER_BAND rows; blocks of clean bands leave at once.
 __global__ void __launch_bounds__(256)
 k_clamp_outside_boxes(float2* __restrict__ vel, const Geom g, int r0, int r1, const __grid_constant__ SplatVBoxes b,
                       const int* __restrict__ over1) {
-    if (*over1 == 0) return;
-    const size_t n = (size_t)(r1 - r0) * g.w;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int ly = r0 + (int)(i / g.w), x = (int)(i % g.w);
+    const int band = blockIdx.y;
+    if (over1[band] == 0) return;
+    const int lo = max(r0, band * OVER_BAND - g.halo), hi = min(r1, (band + 1) * OVER_BAND - g.halo);
+    const int n = (hi - lo) * g.w;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int ly = lo + i / g.w, x = i % g.w;
         bool skip = false;
         for (int k = 0; k < b.n; ++k) skip = skip || in_box(b.b[k], x, g.y0 + ly);
         if (skip) continue;
@@ -365,8 +367,9 @@ k_zero_borders(float2* __restrict__ vel, const Geom g, int r0, int r1) {
 }
 
 // ------------------------------------------------------------------------------------------- gradient
-// ref: shader.SubtractGradient.comp:24-46 via the blocked-neighbour mask; also records whether any
-// |v| > 1 leaves the step (lets the next add_velocity skip its all-cell clamp pass).
+// ref: shader.SubtractGradient.comp:24-46 via the blocked-neighbour mask; also records, per band of
+// OVER_BAND rows, whether any |v| > 1 leaves the step (lets the next add_velocity skip the all-cell clamp
+// for the bands that cannot need it).
 constexpr int GBX = 64, GBY = 4;
 __global__ void __launch_bounds__(GBX * GBY)
 k_gradient_mask(const float2* __restrict__ vin, const float* __restrict__ p, const uint8_t* __restrict__ nbmask,
@@ -385,7 +388,7 @@ k_gradient_mask(const float2* __restrict__ vin, const float* __restrict__ p, con
     v.x = v.x - 0.5f * (x2 - x1);
     v.y = v.y - 0.5f * (y2 - y1);
     vout[pos] = v;
-    if (fabsf(v.x) > 1.0f || fabsf(v.y) > 1.0f) *over1 = 1;
+    if (fabsf(v.x) > 1.0f || fabsf(v.y) > 1.0f) over1[(ly + g.halo) / OVER_BAND] = 1;
 }
 
 // Same, 4 cells per thread (width % 4 == 0): three float4 pressure loads (row, row-1, row+1 - every
@@ -432,7 +435,7 @@ k_gradient_mask4(const float2* __restrict__ vin, const float* __restrict__ p, co
     float4* dst = reinterpret_cast<float4*>(vout + pos);
     stg_stream(dst, make_float4(ox[0], oy[0], ox[1], oy[1]));
     stg_stream(dst + 1, make_float4(ox[2], oy[2], ox[3], oy[3]));
-    if (over) *over1 = 1;
+    if (over) over1[(ly + g.halo) / OVER_BAND] = 1;
 }
 
 }  // namespace
@@ -497,7 +500,9 @@ int launch_splat_velocity_boxes(float2* vel, Geom g, int r0, int r1, const Splat
         b.b[i] = splat_box(splats[i].sx, splats[i].sy, splats[i].r, 0, g.w, g.y0 + r0, g.y0 + r1);
     }
     int launched = 0;
-    k_clamp_outside_boxes<<<sm_count * 4, 256, 0, st>>>(vel, g, r0, r1, b, over1);
+    (void)sm_count;
+    const int nbands = (g.hl + 2 * g.halo + OVER_BAND - 1) / OVER_BAND;
+    k_clamp_outside_boxes<<<dim3(16, nbands, 1), 256, 0, st>>>(vel, g, r0, r1, b, over1);
     ++launched;
     const dim3 grid = boxes_grid(b);
     if (grid.x > 0 && grid.y > 0) {

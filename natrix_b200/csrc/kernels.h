@@ -10,6 +10,7 @@ namespace natrix {
 struct SplatV { float sx, sy, vx, vy, r; };       // add_velocity: splat_pos = pos * size
 struct SplatD { float sx, sy, r, value; };        // add_particles
 constexpr int MAX_SPLATS = 32;                    // per batched launch
+constexpr int OVER_BAND = 64;                     // rows per "some |v| > 1 here" flag (fused.cu)
 struct SplatVBatch { int n; SplatV s[MAX_SPLATS]; };
 struct SplatDBatch { int n; SplatD s[MAX_SPLATS]; };
 
@@ -55,7 +56,7 @@ int launch_dye_advect4(const float* din, float* dout, int pw, int ph, const floa
 // ---- fused pipeline (fused.cu / jacobi_tb.cu) ----------------------------------------------------
 int launch_poisson_mask(const float* pin, const float* div, const uint8_t* nbmask, float* pout,
                         Geom g, int r0, int r1, cudaStream_t st);
-// over1: device int set to non-zero when some |v| > 1 leaves the kernel (see fused.cu)
+// over1: one device int per band of OVER_BAND allocated rows, set when some |v| > 1 is written there
 int launch_gradient_mask(const float2* vin, const float* p, const uint8_t* nbmask, float2* vout,
                          Geom g, int r0, int r1, int* over1, cudaStream_t st);
 // fused advect + vorticity + confinement + [viscosity] + divergence + mask, rows [r0, r1)

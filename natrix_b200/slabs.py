@@ -269,7 +269,8 @@ def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
         algo = jacobi_bytes * w.cells * w.iterations + (116 if w.viscosity == 0 else 132) * w.cells
         line = {
             "metric": metric, "value": value, "unit": metric, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if "strong" in w.name else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w.name, "grid": [w.width, w.height], "per_gpu_grid": [w.width, slab.rows],
                        "jacobi_iterations": w.iterations, "obstacles_per_step": len(w.circles),

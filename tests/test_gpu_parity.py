@@ -253,3 +253,70 @@ def test_config3_4096_fused_equals_reference_order_pipeline():
     W.run_step(w, o, od, 0)
     W.run_step(w, b2, bd2, 0)
     assert_fields_close(W.fields_of(b2, bd2), W.fields_of(o, od), "4096^2 vs C oracle: ", exact=True)
+
+
+def test_dye_vectorised_path_cross_resolution_vs_oracle():
+    """dye width % 4 == 0 takes the 4-cells-per-thread kernel; resolution differs from the velocity grid"""
+    w, h = 200, 120
+    g, o = FluidSimulator(w, h), OracleFluidSimulator(w, h)
+    gd, od = SmoothParticlesArea(336, 252, g), OracleSmoothParticlesArea(336, 252, o)
+    v0 = W.random_velocity(w, h, 6)
+    g.upload("velocity", v0)
+    o.velocity = v0
+    for d in (gd, od):
+        d.dissipation = 0.97
+        d.add_particles((0.5, 0.5), 70.0, 5.0)
+        d.add_particles((0.9, 0.1), 40.0, 1.0)
+    for k in range(3):
+        for s, d in ((g, gd), (o, od)):
+            s.add_circle_obstacle((0.6, 0.4), 15.0)
+            d.update(W.DT)
+            s.update(W.DT)
+            d.update(W.DT)
+            d.add_particles((0.3, 0.3 + 0.1 * k), 20.0, 0.5)
+        err, scale, ndiff = field_report(gd.download(), od.particles)
+        assert ndiff == 0 and scale > 0, (k, err, scale)
+
+
+def test_all_cell_clamp_with_localised_overshoot_vs_oracle():
+    """only a few cells exceed |v| = 1 (one band of rows): add_velocity elsewhere must still clamp them (Q7)"""
+    w, h = 512, 320
+    v0 = (0.4 * W.random_velocity(w, h, 8)).astype(np.float32)
+    v0[200:203, 40:60] = 1.7
+    v0[10, 500] = -3.0
+    g, o = FluidSimulator(w, h), OracleFluidSimulator(w, h)
+    g.upload("velocity", v0)
+    o.velocity = v0
+    for s in (g, o):
+        s.iterations = 9
+        s.add_velocity((0.8, 0.9), (0.2, 0.1), 10.0)
+    assert np.array_equal(g.download("velocity"), o.velocity)
+    for k in range(2):
+        for s in (g, o):
+            s.update(W.DT)
+            s.add_velocity((0.1, 0.1), (0.5, -0.5), 12.0)
+        assert_fields_close(W.fields_of(g), W.fields_of(o), f"step {k}: ", exact=True)
+
+
+def test_results_do_not_depend_on_scheduling_hints(monkeypatch):
+    """chunk heights (obstacle-aware planning, NATRIX_TB_CHUNK / KAPPA) and the launch shape only change
+    how the rows are cut, never a bit of the result"""
+    w, h = 768, 400
+    v0 = W.random_velocity(w, h, 12)
+    outs = []
+    for env in ({}, {"NATRIX_TB_CHUNK": "20"}, {"NATRIX_TB_KAPPA": "3.5", "NATRIX_TB_SHAPE": "0"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        s = FluidSimulator(w, h)
+        s.vorticity, s.viscosity, s.iterations = 1.0, 0.0, 21
+        s.upload("velocity", v0)
+        for _ in range(2):
+            s.add_circle_obstacle((0.5, 0.3), 35.0)
+            s.add_triangle_obstacle((0.1, 0.6), (0.4, 0.65), (0.2, 0.9))
+            s.update(W.DT)
+        outs.append(W.fields_of(s))
+        s.destroy()
+        for k in env:
+            monkeypatch.delenv(k)
+    for other in outs[1:]:
+        assert_fields_close(other, outs[0], exact=True)
