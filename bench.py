@@ -6,10 +6,11 @@
 A "step" is one frame of the reference's demo loop over one synthetic workload (obstacles ->
 FluidSimulator.update -> dye update -> velocity/dye impulses):
 
-* N = 1 (default): config 3 of BASELINE.json - 4096^2 velocity + 4096^2 dye, 100 Jacobi
-  iterations per step, 8 velocity + 8 dye splats and one circular obstacle per step.
-* N > 1 (under torchrun, one rank per GPU): config 5 - weak scaling, one 32768 x 4096 row slab
-  per GPU (global grid 32768 x 4096 N), 200 iterations, 64 circles, halo exchange over NCCL.
+* every N: config 5 of BASELINE.json - weak scaling, one 32768 x 4096 row slab per GPU (global grid
+  32768 x 4096 N), 200 Jacobi iterations per step, 64 circular obstacles per step; N > 1 runs under
+  torchrun, one rank per GPU, halo exchange over NCCL.  The per-N values therefore form ONE series.
+* the N = 1 line also carries `config3_4096`: config 3 - 4096^2 velocity + 4096^2 dye, 100 iterations,
+  8 velocity + 8 dye splats and one circular obstacle per step (`--workload cfg3` makes it the primary).
 
 One JSON line is printed by rank 0.  `value` is device-timed with inputs resident in HBM
 (CUDA events on the simulator's stream, max over ranks); `e2e` is the same metric through the
@@ -163,7 +164,8 @@ def impulse_bytes_per_step(w: W.Workload) -> int:
     return b
 
 
-def run_single_gpu(args, w: W.Workload):
+def measure_single_gpu(args, w: W.Workload, with_cpu: bool, steps: int):
+    """All N = 1 measurements of one workload; returns the JSON-line dict."""
     import torch
 
     from natrix_b200 import _lib as L
@@ -197,7 +199,7 @@ def run_single_gpu(args, w: W.Workload):
     jacobi_ms = []
     torch.cuda.synchronize()
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         W.run_step(w, sim, dye, step); step += 1
     sim.synchronize()            # flushes queued impulses so they are inside the timed region
     ev1.record(stream)
@@ -206,12 +208,12 @@ def run_single_gpu(args, w: W.Workload):
     launches = sim.launch_count - launches0
     stage = sim.timings()        # per-stage CUDA events of the LAST timed step
     jacobi_ms.append(stage["jacobi"])
-    ms_per_step = total_ms / args.steps
+    ms_per_step = total_ms / steps
     value = w.cells / (ms_per_step * 1e-3) / 1e6
 
     # ---- e2e: same steps through the public API, per-step host sync + D2H of a field statistic
     t_e2e = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         t0 = time.perf_counter()
         W.run_step(w, sim, dye, step); step += 1
         ke = sim.stats("velocity")          # kinetic-energy style metric: 32 B device -> host, synchronises
@@ -232,8 +234,8 @@ def run_single_gpu(args, w: W.Workload):
     traffic = None
     tfile = ROOT / "profiles" / "jacobi_traffic.json"
     if tfile.exists():
-        try:
-            traffic = json.loads(tfile.read_text()).get("dram_bytes_per_launch")
+        try:        # ncu dram__bytes_read.sum + dram__bytes_write.sum of one depth-8 launch, per cell
+            traffic = json.loads(tfile.read_text()).get("dram_bytes_per_cell_per_launch") * w.cells
         except Exception:
             traffic = None
     dram_achieved = None if traffic is None or pipeline == 0 else traffic / (jac_ms / jl * 1e-3) / 1e9
@@ -249,13 +251,13 @@ def run_single_gpu(args, w: W.Workload):
 
     # ---- CPU baseline beside it (bounded sample, all host threads)
     cpu = None
-    if not args.no_cpu:
-        _, info = time_cpu_port(w, steps=3, warmup=1, budget_s=25.0)
+    if with_cpu and not args.no_cpu:
+        _, info = time_cpu_port(w, steps=3, warmup=1, budget_s=30.0)
         cpu = {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     step_bytes = w.algorithmic_bytes_per_cell_step() * w.cells
     line = {
-        "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": w.name, "grid": [w.width, w.height], "jacobi_iterations": w.iterations,
@@ -272,6 +274,17 @@ def run_single_gpu(args, w: W.Workload):
         "gpu_launches": int(launches), "clocks": clocks,
         "so": L.loaded_library_path(),
     }
+    sim.destroy()
+    return line
+
+
+def run_single_gpu(args, w: W.Workload, secondary=None):
+    line = measure_single_gpu(args, w, with_cpu=True, steps=args.steps)
+    if secondary is not None:
+        # the 4096^2 configuration the metric also quotes, measured in the same run
+        sub = measure_single_gpu(args, secondary, with_cpu=False, steps=max(args.steps, 20))
+        line["config3_4096"] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "config", "stage_ms", "roofline", "e2e",
+                                                     "gpu_launches")}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -294,8 +307,13 @@ def main(argv=None):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n = max(args.gpus, 1)
     name = args.workload
+    secondary = None
     if name == "auto":
-        name = "cfg3" if n == 1 else "cfg5"
+        # one workload family for every N so that the per-N values form a weak-scaling series:
+        # config 5, 32768 x 4096 cells per GPU.  The N = 1 line also carries config 3 (4096^2).
+        name = "cfg5"
+        if n == 1:
+            secondary = W.cfg3_workload(4096)
     if name == "demo":
         w = W.demo_workload()
     elif name == "cfg2":
@@ -315,7 +333,7 @@ def main(argv=None):
             w = W.cfg5_workload(1)
         return run_reference_arm(args, w)
     if n == 1 and world == 1:
-        return run_single_gpu(args, w)
+        return run_single_gpu(args, w, secondary)
     from natrix_b200 import slabs
 
     return slabs.run_bench(args, w, METRIC, JACOBI_BYTES_PER_CELL_SWEEP, measured_peak_gbs, ClockSampler)

@@ -505,7 +505,7 @@ int natrix_step_phase(natrix_sim* s, int phase, float dt, int sweeps) {
     case 1: return phase_forces(s, dt);
     case 2:
         NEED(sweeps > 0, "sweeps must be positive");
-        stamp(s, ST_JACOBI);
+        if (s->p_is_zero) stamp(s, ST_JACOBI);       // first block of the step: the stage spans all blocks + exchanges
         return phase_jacobi(s, sweeps);
     case 3: {
         if (int rc = phase_project(s)) return rc;

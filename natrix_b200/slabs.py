@@ -196,6 +196,7 @@ def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
     if args.pipeline is not None:
         sim.set_option(L.OPT_PIPELINE, args.pipeline)
     sim.set_option(L.OPT_JACOBI_DEPTH, depth)
+    sim.set_option(L.OPT_TIMING, 1)
     sim.upload("velocity", W.smooth_velocity(w.width, w.height, slab.row0, slab.rows))
 
     def one_step(k):
@@ -228,6 +229,9 @@ def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     launches = sim.launch_count - launches0
+    jac = torch.tensor([sim.timings()["jacobi"]], device=f"cuda:{local}")      # last timed step, incl. halo exchanges
+    dist.all_reduce(jac, op=dist.ReduceOp.MAX)
+    jacobi_ms = float(jac.item())
     ms_per_step = total_ms / args.steps
     value = w.cells / (ms_per_step * 1e-3) / 1e6
 
@@ -284,7 +288,14 @@ def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
             "e2e": {"value": w.cells / (float(e2e_ms.item()) * 1e-3) / 1e6, "unit": metric,
                     "ms_per_step": float(e2e_ms.item()), "h2d_bytes_per_step": 16 * len(w.circles) + 32,
                     "d2h_bytes_per_step": 32},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "cpu_baseline": None,
+            "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": None,
+            "roofline": {"kernel": "k_jacobi_tb (+ pressure halo exchanges)", "bound": "hbm",
+                         "achieved": jacobi_bytes * w.cells * w.iterations / world / (jacobi_ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s per GPU",
+                         "frac": jacobi_bytes * w.cells * w.iterations / world / (jacobi_ms * 1e-3) / 1e9 / peak,
+                         "traffic": None, "jacobi_ms_per_step": jacobi_ms,
+                         "note": "algorithmic 20 B x cells x sweeps per GPU over the Jacobi phase of one step "
+                                 "(max over ranks, halo exchanges included); see the N = 1 line for DRAM traffic"},
             "peak_hbm_gbs": peak, "peak_source": peak_src,
         }
         print(json.dumps(line), flush=True)

@@ -7,7 +7,7 @@ PACKED=${3:-"0 1"}
 mkdir -p "$OUT"
 python scripts/tb_probe.py 1024 512 8 | tail -2
 for shape in $SHAPES; do for packed in $PACKED; do for extra in "" "--no-obstacles"; do
-  NATRIX_TB_SHAPE=$shape timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --packed $packed $extra 2>&1 | python -c "
+  NATRIX_TB_SHAPE=$shape timeout 300 python bench.py --workload cfg3 --steps 10 --warmup 3 --no-cpu --packed $packed $extra 2>&1 | python -c "
 import sys, json
 for line in sys.stdin:
     if line.startswith('{'):
