@@ -60,6 +60,7 @@ struct natrix_sim {
     // bookkeeping
     std::vector<SplatV> pending;                 // add_velocity calls not yet applied (pipeline 1)
     std::vector<int> heavy;                      // merged [lo, hi) local-row intervals stamped with obstacles this step
+    std::vector<int> boxes;                      // (x0, x1, y0, y1) per obstacle stamped this step (scheduling hint)
     bool obs_dirty = false, p_is_zero = false, fused_pre = false;
     int* d_err = nullptr;                        // [0] advection left the slab's halo; [1..] per band of OVER_BAND
                                                  // rows: some |v| > 1 in the READ velocity
@@ -103,8 +104,20 @@ cudaError_t alloc_rows(T** base, T** view, const natrix_sim* s) {
 }
 
 // remember which rows carry obstacles (scheduling hint for the Jacobi kernel); keeps the list merged
-void mark_heavy_rows(natrix_sim* s, double glo, double ghi) {
+void mark_heavy_rows(natrix_sim* s, double glo, double ghi, double xlo = -1e30, double xhi = 1e30) {
     const int margin = 2;
+    {
+        const int bx0 = (int)std::max(0.0, std::floor(xlo) - margin), bx1 = (int)std::min((double)s->g.w, std::ceil(xhi) + margin + 1);
+        const int by0 = std::max((int)std::floor(std::max(glo, -1e9)) - margin - s->g.y0, -s->g.halo);
+        const int by1 = std::min((int)std::ceil(std::min(ghi, 1e9)) + margin + 1 - s->g.y0, s->g.hl + s->g.halo);
+        if (bx1 > bx0 && by1 > by0) {
+            if (s->boxes.size() >= 4 * 256) {        // too many to plan around: one box over everything
+                s->boxes = {0, s->g.w, -s->g.halo, s->g.hl + s->g.halo};
+            } else {
+                s->boxes.insert(s->boxes.end(), {bx0, bx1, by0, by1});
+            }
+        }
+    }
     int lo = (int)std::floor(glo) - margin - s->g.y0, hi = (int)std::ceil(ghi) + margin + 1 - s->g.y0;
     lo = std::max(lo, -s->g.halo);
     hi = std::min(hi, s->g.hl + s->g.halo);
@@ -275,7 +288,7 @@ int phase_jacobi(natrix_sim* s, int sweeps) {
             int t = left < s->jacobi_depth ? left : s->jacobi_depth;
             int n = jacobi_tb_launch(s->tb, s->p[s->pr], s->div, s->nbm, s->p[1 - s->pr], g, t,
                                      s->ext_lo(left - t), s->ext_hi(left - t), s->p_is_zero, s->packed,
-                                     s->heavy.data(), (int)s->heavy.size() / 2, s->st);
+                                     s->boxes.data(), (int)s->boxes.size() / 4, s->st);
             if (n < 0) return fail(NATRIX_ERR_CUDA, std::string("jacobi_tb: ") + jacobi_tb_error(s->tb));
             s->launches += n;
             s->pr = 1 - s->pr;
@@ -312,6 +325,7 @@ int phase_project(natrix_sim* s) {
     }
     s->obs_dirty = false;
     s->heavy.clear();
+    s->boxes.clear();
     stamp(s, ST_COUNT);
     CU(cudaGetLastError());
     return 0;
@@ -473,7 +487,9 @@ int natrix_add_circle_obstacle(natrix_sim* s, float px, float py, float radius, 
     const Geom& g = s->g;
     s->launches += launch_add_circle(s->obs, g, s->ext_lo(g.halo), s->ext_hi(g.halo), px * (float)g.w,
                                      py * (float)g.hg, radius, s->pipeline != 0, s->st);
-    if (radius >= 0.0f) mark_heavy_rows(s, (double)py * g.hg - radius, (double)py * g.hg + radius);
+    if (radius >= 0.0f)
+        mark_heavy_rows(s, (double)py * g.hg - radius, (double)py * g.hg + radius, (double)px * g.w - radius,
+                        (double)px * g.w + radius);
     s->obs_dirty = true;
     CU(cudaGetLastError());
     return 0;
@@ -490,7 +506,10 @@ int natrix_add_triangle_obstacle(natrix_sim* s, float p1x, float p1y, float p2x,
         const double ys[3] = {(double)p1y * g.hg, (double)p2y * g.hg, (double)p3y * g.hg};
         const double ymin = std::min(ys[0], std::min(ys[1], ys[2])), ymax = std::max(ys[0], std::max(ys[1], ys[2]));
         // a degenerate triangle selects whole lines of cells (see stages_ref.cu): call every row heavy
-        if (ymax - ymin < 1.0) mark_heavy_rows(s, 0.0, (double)g.hg); else mark_heavy_rows(s, ymin, ymax);
+        const double xs[3] = {(double)p1x * g.w, (double)p2x * g.w, (double)p3x * g.w};
+        const double xmin = std::min(xs[0], std::min(xs[1], xs[2])), xmax = std::max(xs[0], std::max(xs[1], xs[2]));
+        if (ymax - ymin < 1.0 || xmax - xmin < 1.0) mark_heavy_rows(s, 0.0, (double)g.hg);
+        else mark_heavy_rows(s, ymin, ymax, xmin, xmax);
     }
     s->obs_dirty = true;
     CU(cudaGetLastError());

@@ -77,9 +77,8 @@ struct TBParams {
     int w;            // grid width
     int halo;         // tensor-map row = local row + halo
     int r0, r1;       // output rows [r0, r1)
-    const int* chunk_lo;  // [nchunks + 1] first output row of every chunk (device memory)
-    int nstrips;      // strips per chunk
-    int ntiles;       // nstrips * nchunks
+    const int4* tiles;    // [ntiles] (strip, first output row, end output row, -) in device memory
+    int ntiles;
     int hx;           // halo columns on each side of a strip (>= T, multiple of 4)
 };
 
@@ -245,10 +244,9 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
     if (tile >= prm.ntiles) return;                 // warps are independent: no block barrier below
     WarpSmem& S = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
 
-    const int chunk = tile / prm.nstrips, strip = tile - chunk * prm.nstrips;
+    const int4 td = prm.tiles[tile];
+    const int strip = td.x, out_lo = td.y, out_hi = td.z;
     const int x0 = strip * (SW - 2 * prm.hx) - prm.hx;      // first strip column (may be < 0)
-    const int out_lo = prm.chunk_lo[chunk];
-    const int out_hi = prm.chunk_lo[chunk + 1];
     const int y_first = out_lo - T;                          // first input row (local)
     const int nrows = (out_hi - out_lo) + 2 * T;
     const int ngroups = (nrows + GROUP - 1) / GROUP;   // extra rows of the last group are computed and dropped
@@ -400,71 +398,93 @@ struct JacobiTB {
     int sm_count = 148;
     int chunk_override = 0;
     std::vector<MapEntry> maps;
-    // Chunk plans: where the output rows are cut.  Rows that carry obstacles cost about `kappa` times a
-    // free row (select body), so chunks are shorter there and every tile takes about the same time.
+    // Tile plans: how the output cells are cut into one tile per resident warp.  Rows of a strip that
+    // carry obstacles (from the boxes the host stamped this step) cost about `kappa` times a free row
+    // (select body), so tiles are cut shorter there and every tile takes about the same time.
     struct Plan {
-        std::vector<int> key;         // r0, r1, depth, max chunks, heavy intervals...
-        std::vector<int> lo;          // nchunks + 1 boundaries
-        int* d_lo = nullptr;
+        std::vector<int> key;         // geometry + obstacle boxes
+        std::vector<int4> tiles;
+        int4* d_tiles = nullptr;
     };
     std::vector<Plan> plans;
-    double kappa = 1.6;           // measured at 4096^2 with one r = 256 circle: 1.0 -> 1.21 ms, 1.6 -> 0.83 ms, 2.0 -> 0.88 ms per 100 sweeps
+    double kappa = 2.0;           // measured: 32768x4096, 64 circles, 200 sweeps: 1.6 -> 13.8 ms, 2.0 -> 11.9 ms, 2.5 -> 13.2 ms (9.3 ms without obstacles)
 
-    static std::vector<int> cut_rows(int r0, int r1, const int* heavy, int nheavy, int depth, int max_chunks,
-                                     double kappa) {
-        const int rows = r1 - r0;
-        std::vector<float> cost(rows + 1, 0.0f);
-        std::vector<int> nh(rows + 1, 0);
-        std::vector<char> is_heavy(rows, 0);
-        for (int k = 0; k < nheavy; ++k)
-            for (int y = std::max(heavy[2 * k], r0); y < std::min(heavy[2 * k + 1], r1); ++y) is_heavy[y - r0] = 1;
-        for (int y = 0; y < rows; ++y) {
-            cost[y + 1] = cost[y] + (is_heavy[y] ? (float)kappa : 1.0f);
-            nh[y + 1] = nh[y] + is_heavy[y];
+    static constexpr int PU = 8;  // planning granularity (rows)
+
+    // boxes: nboxes x (x0, x1, y0, y1), global columns, local rows, half-open.
+    static std::vector<int4> cut_tiles(int w, int r0, int r1, int hx, int depth, const int* boxes, int nboxes,
+                                       int max_tiles, double kappa, int chunk_override) {
+        const int pitch = SW - 2 * hx, nstrips = (w + pitch - 1) / pitch;
+        const int rows = r1 - r0, nu = (rows + PU - 1) / PU;
+        // heavy[s][u]: prefix count of planning units of strip s that overlap an obstacle box
+        std::vector<int> pre((size_t)nstrips * (nu + 1), 0);
+        std::vector<char> mark(nu);
+        for (int st_ = 0; st_ < nstrips; ++st_) {
+            const int c0 = st_ * pitch - hx - 1, c1 = st_ * pitch - hx + SW + 1;   // columns whose masks the strip reads
+            std::fill(mark.begin(), mark.end(), 0);
+            for (int k = 0; k < nboxes; ++k) {
+                const int* bx = boxes + 4 * k;
+                if (bx[1] <= c0 || bx[0] >= c1) continue;
+                const int ya = std::max(bx[2] - 1, r0), yb = std::min(bx[3] + 1, r1);
+                for (int u = (ya - r0) / PU; u < nu && r0 + u * PU < yb; ++u) mark[u] = 1;
+            }
+            int* p = &pre[(size_t)st_ * (nu + 1)];
+            for (int u = 0; u < nu; ++u) p[u + 1] = p[u] + mark[u];
         }
-        auto tile_cost = [&](int a, int b) {     // rows [a, b) plus the 2 * depth warm-up rows
-            return (cost[b] - cost[a]) + 2.0f * depth * (nh[b] - nh[a] > 0 ? (float)kappa : 1.0f);
+        auto cost = [&](int st_, int ua, int ub) {       // planning units [ua, ub) of one strip + warm-up rows
+            const int* p = &pre[(size_t)st_ * (nu + 1)];
+            const int hv = p[ub] - p[ua];
+            return (double)(ub - ua) * PU + (kappa - 1.0) * hv * PU + 2.0 * depth * (hv > 0 ? kappa : 1.0);
         };
-        auto cut = [&](float limit, std::vector<int>* out) {
-            int n = 0, a = 0;
-            if (out) out->assign(1, r0);
-            while (a < rows) {
-                int b = std::min(rows, a + 4);
-                while (b < rows && tile_cost(a, std::min(rows, b + 4)) <= limit) b = std::min(rows, b + 4);
-                if (out) out->push_back(r0 + b);
-                a = b;
-                ++n;
+        auto cut = [&](double limit, std::vector<int4>* out) {
+            int n = 0;
+            for (int st_ = 0; st_ < nstrips; ++st_) {
+                int ua = 0;
+                while (ua < nu) {
+                    int lo = ua + 1, hi = nu;               // largest ub with cost <= limit (at least one unit)
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) / 2;
+                        if (cost(st_, ua, mid) <= limit) lo = mid; else hi = mid - 1;
+                    }
+                    if (out) out->push_back(make_int4(st_, r0 + ua * PU, std::min(r1, r0 + lo * PU), 0));
+                    ua = lo;
+                    ++n;
+                }
             }
             return n;
         };
-        float lo = 0.0f, hi = tile_cost(0, rows);
-        for (int it = 0; it < 30; ++it) {
-            const float mid = 0.5f * (lo + hi);
-            if (cut(mid, nullptr) <= max_chunks) hi = mid; else lo = mid;
+        std::vector<int4> tiles;
+        if (chunk_override > 0) {
+            for (int y = r0; y < r1; y += chunk_override)
+                for (int st_ = 0; st_ < nstrips; ++st_) tiles.push_back(make_int4(st_, y, std::min(r1, y + chunk_override), 0));
+            return tiles;
         }
-        std::vector<int> out;
-        cut(hi, &out);
-        return out;
+        double lo = 0.0, hi = 0.0;
+        for (int st_ = 0; st_ < nstrips; ++st_) hi = std::max(hi, cost(st_, 0, nu));
+        for (int it = 0; it < 24; ++it) {
+            const double mid = 0.5 * (lo + hi);
+            if (cut(mid, nullptr) <= max_tiles) hi = mid; else lo = mid;
+        }
+        cut(hi, &tiles);
+        // neighbouring warps should stream neighbouring strips of the same rows
+        std::stable_sort(tiles.begin(), tiles.end(), [](const int4& a, const int4& b) { return a.y < b.y; });
+        return tiles;
     }
 
-    const Plan* plan_for(int r0, int r1, const int* heavy, int nheavy, int depth, int max_chunks, cudaStream_t st) {
-        std::vector<int> key = {r0, r1, depth, max_chunks, chunk_override};
-        key.insert(key.end(), heavy, heavy + 2 * nheavy);
+    const Plan* plan_for(int w, int r0, int r1, int hx, int depth, const int* boxes, int nboxes, int max_tiles,
+                         cudaStream_t st) {
+        std::vector<int> key = {w, r0, r1, hx, depth, max_tiles, chunk_override};
+        key.insert(key.end(), boxes, boxes + 4 * nboxes);
         for (const Plan& p : plans)
             if (p.key == key) return &p;
         Plan p;
         p.key = key;
-        if (chunk_override > 0) {
-            for (int y = r0; y < r1; y += chunk_override) p.lo.push_back(y);
-            p.lo.push_back(r1);
-        } else {
-            p.lo = cut_rows(r0, r1, heavy, nheavy, depth, max_chunks, kappa);
-        }
-        if (cudaMalloc((void**)&p.d_lo, p.lo.size() * sizeof(int)) != cudaSuccess) { err = "cudaMalloc(chunk plan)"; return nullptr; }
-        if (cudaMemcpyAsync(p.d_lo, p.lo.data(), p.lo.size() * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess ||
-            cudaStreamSynchronize(st) != cudaSuccess) { err = "chunk plan upload failed"; cudaFree(p.d_lo); return nullptr; }
+        p.tiles = cut_tiles(w, r0, r1, hx, depth, boxes, nboxes, max_tiles, kappa, chunk_override);
+        if (cudaMalloc((void**)&p.d_tiles, p.tiles.size() * sizeof(int4)) != cudaSuccess) { err = "cudaMalloc(tile plan)"; return nullptr; }
+        if (cudaMemcpyAsync(p.d_tiles, p.tiles.data(), p.tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { err = "tile plan upload failed"; cudaFree(p.d_tiles); return nullptr; }
         if (plans.size() >= 16) {                 // evict the oldest; the stream is idle after the sync above
-            cudaFree(plans.front().d_lo);
+            cudaFree(plans.front().d_tiles);
             plans.erase(plans.begin());
         }
         plans.push_back(std::move(p));
@@ -521,7 +541,7 @@ JacobiTB* jacobi_tb_create() {
 
 void jacobi_tb_destroy(JacobiTB* tb) {
     if (!tb) return;
-    for (auto& p : tb->plans) cudaFree(p.d_lo);
+    for (auto& p : tb->plans) cudaFree(p.d_tiles);
     delete tb;
 }
 const char* jacobi_tb_error(JacobiTB* tb) { return tb ? tb->err.c_str() : "null JacobiTB"; }
@@ -532,7 +552,7 @@ bool jacobi_tb_supported(const Geom& g) {
 }
 
 int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div, const uint8_t* nbmask, float* pout, Geom g,
-                     int depth, int r0, int r1, bool p_is_zero, int packed, const int* heavy_rows, int nheavy,
+                     int depth, int r0, int r1, bool p_is_zero, int packed, const int* boxes, int nboxes,
                      cudaStream_t st) {
     if (!tb) return -1;
     if (depth < 1 || depth > JACOBI_TB_MAX_DEPTH) { tb->err = "depth out of range"; return -1; }
@@ -559,15 +579,12 @@ int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div, const uin
     prm.r0 = r0;
     prm.r1 = r1;
     prm.hx = depth <= 4 ? 4 : 8;
-    prm.nstrips = (g.w + (SW - 2 * prm.hx) - 1) / (SW - 2 * prm.hx);
-    // about one tile per resident warp; chunk heights follow the obstacle rows (see Plan)
-    int max_chunks = (tb->sm_count * warps * (tb->shape == 0 ? 2 : 1)) / prm.nstrips;
-    if (max_chunks < 1) max_chunks = 1;
-    const JacobiTB::Plan* plan = tb->plan_for(r0, r1, heavy_rows, nheavy, depth, max_chunks, st);
+    // one tile per resident warp; tile heights follow the obstacle boxes (see Plan)
+    const int max_tiles = tb->sm_count * warps * (tb->shape == 0 ? 2 : 1);
+    const JacobiTB::Plan* plan = tb->plan_for(g.w, r0, r1, prm.hx, depth, boxes, nboxes, max_tiles, st);
     if (!plan) return -1;
-    prm.chunk_lo = plan->d_lo;
-    const int nchunks = (int)plan->lo.size() - 1;
-    prm.ntiles = prm.nstrips * nchunks;
+    prm.tiles = plan->d_tiles;
+    prm.ntiles = (int)plan->tiles.size();
     const int blocks = (prm.ntiles + warps - 1) / warps;
 
     KernelFn fn = kernel_for(depth, p_is_zero, packed != 0, tb->shape);

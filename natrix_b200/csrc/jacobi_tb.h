@@ -18,11 +18,12 @@ bool jacobi_tb_supported(const Geom& g);
 // Runs `depth` (1..JACOBI_TB_MAX_DEPTH) Jacobi sweeps pin -> pout for local rows [r0, r1).
 // pin / div / nbmask must be valid on rows [r0-depth, r1+depth) clipped to the global domain.
 // p_is_zero: pin is known to be all zero (first block of a step), so it is not read.
-// heavy_rows: nheavy pairs [lo, hi) of local rows that carry obstacles this step (a scheduling hint
-// only: chunks are cut shorter there; results never depend on it).
+// boxes: nboxes x (x0, x1, y0, y1) bounding boxes (global columns, local rows, half-open) of the
+// obstacles stamped this step - a scheduling hint only: tiles are cut shorter where the select body
+// will run; results never depend on it.
 // Returns the number of kernels launched, or -1 on error (see jacobi_tb_error).
 int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div, const uint8_t* nbmask,
                      float* pout, Geom g, int depth, int r0, int r1, bool p_is_zero, int packed,
-                     const int* heavy_rows, int nheavy, cudaStream_t st);
+                     const int* boxes, int nboxes, cudaStream_t st);
 
 }  // namespace natrix
