@@ -233,6 +233,51 @@ __device__ __forceinline__ void row_step2(float2 (&a)[T][2][2], const LaneAddr& 
     out[0] = nw[0]; out[1] = nw[1];
 }
 
+// Select-free packed row step in two phases.  Phase A forms (x1 + x2) + y1 of EVERY level from the rows
+// kept from earlier iterations - nothing in it depends on this iteration's new rows, and after it the
+// "older" slot of every level is dead.  Phase B is the short dependent chain through the levels
+// (+ y2, - b, * 0.25): each level's new row can be written straight into the dead slot of the level
+// below, so the state rotates without register moves.
+template <int T, bool PZERO, int PAR>
+__device__ __forceinline__ void row_step2_fast(float2 (&a)[T][2][2], const LaneAddr& sa, int i, int lane,
+                                               float2 (&out)[2]) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const float2 quarter = make_float2(0.25f, 0.25f);
+    const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
+    float2 part[T][2];
+#pragma unroll
+    for (int t = 1; t <= T; ++t) {
+        const float2(&old)[2] = a[t - 1][PAR];
+        const float2(&mid)[2] = a[t - 1][PAR ^ 1];
+        const float sl = bitsel(mid[0].x, __shfl_sync(FULL, mid[1].y, lane_l), sa.edge_l);
+        const float sr = bitsel(mid[1].y, __shfl_sync(FULL, mid[0].x, lane_r), sa.edge_r);
+        const float2 s0 = make_float2(sl + mid[0].y, mid[0].x + mid[1].x);
+        const float2 s1 = make_float2(mid[0].y + mid[1].y, mid[1].x + sr);
+        part[t - 1][0] = __fadd2_rn(s0, old[0]);
+        part[t - 1][1] = __fadd2_rn(s1, old[1]);
+    }
+    float2 nw0, nw1;
+    if (PZERO) {
+        nw0 = nw1 = make_float2(0.0f, 0.0f);
+    } else {
+        const float4 v = lds128(sa.p + (uint32_t)(i & (P_ROWS - 1)) * (SW * 4));
+        nw0 = make_float2(v.x, v.y);
+        nw1 = make_float2(v.z, v.w);
+    }
+#pragma unroll
+    for (int t = 1; t <= T; ++t) {
+        const float4 dv = lds128(sa.d + (uint32_t)((i - t) & (D_ROWS - 1)) * (SW * 4));
+        const float2 r0 = __fmul2_rn(__fadd2_rn(__fadd2_rn(part[t - 1][0], nw0), neg2(make_float2(dv.x, dv.y))), quarter);
+        const float2 r1 = __fmul2_rn(__fadd2_rn(__fadd2_rn(part[t - 1][1], nw1), neg2(make_float2(dv.z, dv.w))), quarter);
+        a[t - 1][PAR][0] = nw0;
+        a[t - 1][PAR][1] = nw1;
+        nw0 = r0;
+        nw1 = r1;
+    }
+    out[0] = nw0;
+    out[1] = nw1;
+}
+
 template <int T, bool PZERO, bool PACKED, int V>
 __global__ void __launch_bounds__(Shape<V>::WARPS * 32, Shape<V>::BLOCKS)
 k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_d,
@@ -305,7 +350,8 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
         constexpr bool SLOW = decltype(slow)::value;
         if constexpr (PACKED) {
             float2 r[2];
-            row_step2<T, PZERO, PAR, SLOW>(a2, sa, i, lane, r);
+            if constexpr (SLOW) row_step2<T, PZERO, PAR, true>(a2, sa, i, lane, r);
+            else row_step2_fast<T, PZERO, PAR>(a2, sa, i, lane, r);
             store_row(i, r[0].x, r[0].y, r[1].x, r[1].y);
         } else {
             float r[4];
