@@ -104,9 +104,14 @@ cudaError_t alloc_rows(T** base, T** view, const natrix_sim* s) {
 }
 
 // remember which rows carry obstacles (scheduling hint for the Jacobi kernel); keeps the list merged
-void mark_heavy_rows(natrix_sim* s, double glo, double ghi, double xlo = -1e30, double xhi = 1e30) {
+void mark_heavy_rows(natrix_sim* s, double glo, double ghi, double xlo = -1e30, double xhi = 1e30, bool circle = false) {
     const int margin = 2;
-    {
+    if (circle && s->boxes.size() < 4 * 256) {
+        // a circle keeps its geometry: (cx, -1 - r, cy local, 0), see jacobi_tb.h
+        const double r = 0.5 * (ghi - glo);
+        s->boxes.insert(s->boxes.end(), {(int)std::lround(0.5 * (xlo + xhi)), -1 - (int)std::ceil(r),
+                                         (int)std::lround(0.5 * (glo + ghi)) - s->g.y0, 0});
+    } else {
         const int bx0 = (int)std::max(0.0, std::floor(xlo) - margin), bx1 = (int)std::min((double)s->g.w, std::ceil(xhi) + margin + 1);
         const int by0 = std::max((int)std::floor(std::max(glo, -1e9)) - margin - s->g.y0, -s->g.halo);
         const int by1 = std::min((int)std::ceil(std::min(ghi, 1e9)) + margin + 1 - s->g.y0, s->g.hl + s->g.halo);
@@ -489,7 +494,7 @@ int natrix_add_circle_obstacle(natrix_sim* s, float px, float py, float radius, 
                                      py * (float)g.hg, radius, s->pipeline != 0, s->st);
     if (radius >= 0.0f)
         mark_heavy_rows(s, (double)py * g.hg - radius, (double)py * g.hg + radius, (double)px * g.w - radius,
-                        (double)px * g.w + radius);
+                        (double)px * g.w + radius, true);
     s->obs_dirty = true;
     CU(cudaGetLastError());
     return 0;
