@@ -123,9 +123,10 @@ struct LaneAddr { uint32_t p, d, m, edge_l, edge_r, mkeep; };
 
 // blocked-neighbour bits (one byte per column) of input row i for this lane's 4 columns, straight
 // from the TMA-filled ring; the grid-edge L / R bits are dropped (handled through edge_l / edge_r)
-__device__ __forceinline__ uint32_t mask_of_row(const LaneAddr& sa, int i) {
-    return lds32(sa.m + (uint32_t)((i >> 2) & (M_SLOTS - 1)) * M_SLOT + (uint32_t)(i & 3) * MBOX) & sa.mkeep;
+__device__ __forceinline__ uint32_t raw_mask_of_row(const LaneAddr& sa, int i) {
+    return lds32(sa.m + (uint32_t)((i >> 2) & (M_SLOTS - 1)) * M_SLOT + (uint32_t)(i & 3) * MBOX);
 }
+__device__ __forceinline__ uint32_t mask_of_row(const LaneAddr& sa, int i) { return raw_mask_of_row(sa, i) & sa.mkeep; }
 
 // One input row: advance every time level by one row.  a[t][.] holds the two newest rows of
 // level t (slot PAR = older, PAR^1 = newer); afterwards slot PAR holds the newest.
@@ -279,6 +280,35 @@ __device__ __forceinline__ void row_step2_fast(float2 (&a)[T][2][2], const LaneA
     out[1] = nw1;
 }
 
+// Rows deep inside an obstacle: every cell of the strip has all four neighbours blocked, in every row in
+// flight, so each level is ((C + C) + C) + C - b, * 0.25 of the cell itself (shader.Poisson.comp:32-37 with
+// all four substitutions): no neighbours, no shuffles, no selects.
+template <int T, bool PZERO, int PAR>
+__device__ __forceinline__ void row_step2_solid(float2 (&a)[T][2][2], const LaneAddr& sa, int i, float2 (&out)[2]) {
+    const float2 quarter = make_float2(0.25f, 0.25f);
+    float2 nw0, nw1;
+    if (PZERO) {
+        nw0 = nw1 = make_float2(0.0f, 0.0f);
+    } else {
+        const float4 v = lds128(sa.p + (uint32_t)(i & (P_ROWS - 1)) * (SW * 4));
+        nw0 = make_float2(v.x, v.y);
+        nw1 = make_float2(v.z, v.w);
+    }
+#pragma unroll
+    for (int t = 1; t <= T; ++t) {
+        const float2 c0 = a[t - 1][PAR ^ 1][0], c1 = a[t - 1][PAR ^ 1][1];
+        const float4 dv = lds128(sa.d + (uint32_t)((i - t) & (D_ROWS - 1)) * (SW * 4));
+        const float2 r0 = __fmul2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(c0, c0), c0), c0), neg2(make_float2(dv.x, dv.y))), quarter);
+        const float2 r1 = __fmul2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(c1, c1), c1), c1), neg2(make_float2(dv.z, dv.w))), quarter);
+        a[t - 1][PAR][0] = nw0;
+        a[t - 1][PAR][1] = nw1;
+        nw0 = r0;
+        nw1 = r1;
+    }
+    out[0] = nw0;
+    out[1] = nw1;
+}
+
 template <int T, bool PZERO, bool PACKED, int V>
 __global__ void __launch_bounds__(Shape<V>::WARPS * 32, Shape<V>::BLOCKS)
 k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_d,
@@ -346,17 +376,31 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
         if (st_ok && ly >= out_lo && ly < out_hi)
             stg_stream(reinterpret_cast<float4*>(out_col + (ptrdiff_t)ly * prm.w), make_float4(r0, r1, r2, r3));
     };
-    auto one_row = [&](auto par, auto slow, int i) {
+    uint32_t solid = 0u;                              // bit t-1: every cell of row i-t (whole strip) is fully blocked
+    auto fast_row = [&](auto par, int i) {            // no row in flight has mask bits
         constexpr int PAR = decltype(par)::value;
-        constexpr bool SLOW = decltype(slow)::value;
         if constexpr (PACKED) {
             float2 r[2];
-            if constexpr (SLOW) row_step2<T, PZERO, PAR, true>(a2, sa, i, lane, r);
-            else row_step2_fast<T, PZERO, PAR>(a2, sa, i, lane, r);
+            row_step2_fast<T, PZERO, PAR>(a2, sa, i, lane, r);
             store_row(i, r[0].x, r[0].y, r[1].x, r[1].y);
         } else {
             float r[4];
-            row_step<T, PZERO, PAR, SLOW>(a, sa, i, lane, r);
+            row_step<T, PZERO, PAR, false>(a, sa, i, lane, r);
+            store_row(i, r[0], r[1], r[2], r[3]);
+        }
+    };
+    auto one_row = [&](auto par, int i) {             // picks the body from the history of the rows in flight
+        constexpr int PAR = decltype(par)::value;
+        if (!busy) {
+            fast_row(par, i);
+        } else if constexpr (PACKED) {
+            float2 r[2];
+            if (solid == BUSY_MASK) row_step2_solid<T, PZERO, PAR>(a2, sa, i, r);
+            else row_step2<T, PZERO, PAR, true>(a2, sa, i, lane, r);
+            store_row(i, r[0].x, r[0].y, r[1].x, r[1].y);
+        } else {
+            float r[4];
+            row_step<T, PZERO, PAR, true>(a, sa, i, lane, r);
             store_row(i, r[0], r[1], r[2], r[3]);
         }
     };
@@ -370,26 +414,30 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
     for (int g = 0; g < ngroups; ++g) {
         while (!mbar_try_wait(bar0 + 8 * (g & (NBAR - 1)), (g / NBAR) & 1)) {}
         const int i0 = GROUP * g;
-        const uint32_t m0 = mask_of_row(sa, i0), m1 = mask_of_row(sa, i0 + 1);
-        const uint32_t m2 = mask_of_row(sa, i0 + 2), m3 = mask_of_row(sa, i0 + 3);
-        const uint32_t a0 = __any_sync(0xffffffffu, m0 != 0u) ? 1u : 0u, a1 = __any_sync(0xffffffffu, m1 != 0u) ? 1u : 0u;
-        const uint32_t a2_ = __any_sync(0xffffffffu, m2 != 0u) ? 1u : 0u, a3 = __any_sync(0xffffffffu, m3 != 0u) ? 1u : 0u;
+        const uint32_t w0 = raw_mask_of_row(sa, i0), w1 = raw_mask_of_row(sa, i0 + 1);
+        const uint32_t w2 = raw_mask_of_row(sa, i0 + 2), w3 = raw_mask_of_row(sa, i0 + 3);
+        const uint32_t a0 = __any_sync(0xffffffffu, (w0 & sa.mkeep) != 0u) ? 1u : 0u, a1 = __any_sync(0xffffffffu, (w1 & sa.mkeep) != 0u) ? 1u : 0u;
+        const uint32_t a2_ = __any_sync(0xffffffffu, (w2 & sa.mkeep) != 0u) ? 1u : 0u, a3 = __any_sync(0xffffffffu, (w3 & sa.mkeep) != 0u) ? 1u : 0u;
         if (lane == 0 && g + 1 < ngroups) issue(g + 1);
         if (busy | a0 | a1 | a2_ | a3) {
-            // some row in flight (or arriving) carries mask bits: select body for the rows that need it
-            if (busy) one_row(I0{}, std::true_type{}, i0); else one_row(I0{}, std::false_type{}, i0);
-            busy = ((busy << 1) | a0) & BUSY_MASK;
-            if (busy) one_row(I1{}, std::true_type{}, i0 + 1); else one_row(I1{}, std::false_type{}, i0 + 1);
-            busy = ((busy << 1) | a1) & BUSY_MASK;
-            if (busy) one_row(I0{}, std::true_type{}, i0 + 2); else one_row(I0{}, std::false_type{}, i0 + 2);
-            busy = ((busy << 1) | a2_) & BUSY_MASK;
-            if (busy) one_row(I1{}, std::true_type{}, i0 + 3); else one_row(I1{}, std::false_type{}, i0 + 3);
-            busy = ((busy << 1) | a3) & BUSY_MASK;
+            // some row in flight (or arriving) carries mask bits: per row, the body its rows in flight need
+            constexpr uint32_t ALL = 0x0f0f0f0fu;
+            const uint32_t s0 = __all_sync(0xffffffffu, (w0 & ALL) == ALL) ? 1u : 0u, s1 = __all_sync(0xffffffffu, (w1 & ALL) == ALL) ? 1u : 0u;
+            const uint32_t s2 = __all_sync(0xffffffffu, (w2 & ALL) == ALL) ? 1u : 0u, s3 = __all_sync(0xffffffffu, (w3 & ALL) == ALL) ? 1u : 0u;
+            one_row(I0{}, i0);
+            busy = ((busy << 1) | a0) & BUSY_MASK; solid = ((solid << 1) | s0) & BUSY_MASK;
+            one_row(I1{}, i0 + 1);
+            busy = ((busy << 1) | a1) & BUSY_MASK; solid = ((solid << 1) | s1) & BUSY_MASK;
+            one_row(I0{}, i0 + 2);
+            busy = ((busy << 1) | a2_) & BUSY_MASK; solid = ((solid << 1) | s2) & BUSY_MASK;
+            one_row(I1{}, i0 + 3);
+            busy = ((busy << 1) | a3) & BUSY_MASK; solid = ((solid << 1) | s3) & BUSY_MASK;
         } else {
+            solid = 0u;
 #pragma unroll 1
             for (int h = 0; h < GROUP; h += 2) {
-                one_row(I0{}, std::false_type{}, i0 + h);
-                one_row(I1{}, std::false_type{}, i0 + h + 1);
+                fast_row(I0{}, i0 + h);
+                fast_row(I1{}, i0 + h + 1);
             }
         }
     }
@@ -463,38 +511,60 @@ struct JacobiTB {
                                        int max_tiles, double kappa, int chunk_override) {
         const int pitch = SW - 2 * hx, nstrips = (w + pitch - 1) / pitch;
         const int rows = r1 - r0, nu = (rows + PU - 1) / PU;
-        // heavy[s][u]: prefix count of planning units of strip s that overlap an obstacle box
-        std::vector<int> pre((size_t)nstrips * (nu + 1), 0);
+        // per strip, prefix counts of planning units that will run the select body ("heavy": some cell
+        // of the strip has a blocked neighbour) or the neighbour-free body ("solid": the strip is wholly
+        // inside a circle there, with `depth` rows of margin for the rows in flight)
+        std::vector<int> pre((size_t)nstrips * (nu + 1), 0), pres((size_t)nstrips * (nu + 1), 0);
         std::vector<char> mark(nu);
         for (int st_ = 0; st_ < nstrips; ++st_) {
             const int c0 = st_ * pitch - hx - 1, c1 = st_ * pitch - hx + SW + 1;   // columns whose masks the strip reads
             std::fill(mark.begin(), mark.end(), 0);
-            for (int k = 0; k < nboxes; ++k) {
-                const int* bx = boxes + 4 * k;
-                int ya, yb;
-                if (bx[1] < bx[0]) {
-                    // circle (cx, -1 - r, cy, -): only the rows where it really crosses this strip's columns
-                    const double cx = bx[0], rr = (double)(-1 - bx[1]) + 2.0, cy = bx[2];
-                    const double dx = std::max(0.0, std::max((double)c0 - cx, cx - (double)(c1 - 1)));
-                    if (dx > rr) continue;
-                    const double hh = std::sqrt(rr * rr - dx * dx);
-                    ya = std::max((int)std::floor(cy - hh) - 1, r0);
-                    yb = std::min((int)std::ceil(cy + hh) + 2, r1);
-                } else {
-                    if (bx[1] <= c0 || bx[0] >= c1) continue;
-                    ya = std::max(bx[2] - 1, r0);
-                    yb = std::min(bx[3] + 1, r1);
+            for (int pass = 0; pass < 2; ++pass) {           // pass 0: heavy rows, pass 1: solid rows override
+                for (int k = 0; k < nboxes; ++k) {
+                    const int* bx = boxes + 4 * k;
+                    int ya, yb;
+                    if (bx[1] < bx[0]) {
+                        // circle (cx, -1 - r, cy, -): only the rows where it really crosses this strip's columns
+                        const double cx = bx[0], r = (double)(-1 - bx[1]), cy = bx[2];
+                        if (pass == 0) {
+                            const double rr = r + 2.0;
+                            const double dx = std::max(0.0, std::max((double)c0 - cx, cx - (double)(c1 - 1)));
+                            if (dx > rr) continue;
+                            const double hh = std::sqrt(rr * rr - dx * dx);
+                            ya = std::max((int)std::floor(cy - hh) - 1, r0);
+                            yb = std::min((int)std::ceil(cy + hh) + 2, r1);
+                        } else {
+                            const double rr = r - 2.0;
+                            const double dmax = std::max(std::fabs((double)c0 - cx), std::fabs((double)(c1 - 1) - cx));
+                            if (c0 < 0 || c1 > w || dmax >= rr) continue;
+                            const double hf = std::sqrt(rr * rr - dmax * dmax) - depth - 1;
+                            ya = std::max((int)std::ceil(cy - hf), r0);
+                            yb = std::min((int)std::floor(cy + hf), r1);
+                        }
+                    } else {
+                        if (pass == 1 || bx[1] <= c0 || bx[0] >= c1) continue;
+                        ya = std::max(bx[2] - 1, r0);
+                        yb = std::min(bx[3] + 1, r1);
+                    }
+                    if (yb <= ya) continue;
+                    if (pass == 0) {
+                        for (int u = (ya - r0) / PU; u < nu && r0 + u * PU < yb; ++u) mark[u] = 1;
+                    } else {                                 // only units lying wholly inside
+                        for (int u = (ya - r0 + PU - 1) / PU; u < nu && r0 + (u + 1) * PU <= yb; ++u) mark[u] = 2;
+                    }
                 }
-                if (yb <= ya) continue;
-                for (int u = (ya - r0) / PU; u < nu && r0 + u * PU < yb; ++u) mark[u] = 1;
             }
             int* p = &pre[(size_t)st_ * (nu + 1)];
-            for (int u = 0; u < nu; ++u) p[u + 1] = p[u] + mark[u];
+            int* q = &pres[(size_t)st_ * (nu + 1)];
+            for (int u = 0; u < nu; ++u) { p[u + 1] = p[u] + (mark[u] == 1); q[u + 1] = q[u] + (mark[u] == 2); }
         }
+        constexpr double SIGMA = 0.8;                    // cost of a neighbour-free row relative to a free row
         auto cost = [&](int st_, int ua, int ub) {       // planning units [ua, ub) of one strip + warm-up rows
             const int* p = &pre[(size_t)st_ * (nu + 1)];
-            const int hv = p[ub] - p[ua];
-            return (double)(ub - ua) * PU + (kappa - 1.0) * hv * PU + 2.0 * depth * (hv > 0 ? kappa : 1.0);
+            const int* q = &pres[(size_t)st_ * (nu + 1)];
+            const int hv = p[ub] - p[ua], so = q[ub] - q[ua];
+            return (double)(ub - ua) * PU + (kappa - 1.0) * hv * PU + (SIGMA - 1.0) * so * PU +
+                   2.0 * depth * (hv > 0 ? kappa : 1.0);
         };
         auto cut = [&](double limit, std::vector<int4>* out) {
             int n = 0;
