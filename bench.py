@@ -234,8 +234,10 @@ def measure_single_gpu(args, w: W.Workload, with_cpu: bool, steps: int):
     traffic = None
     tfile = ROOT / "profiles" / "jacobi_traffic.json"
     if tfile.exists():
-        try:        # ncu dram__bytes_read.sum + dram__bytes_write.sum of one depth-8 launch, per cell
-            traffic = json.loads(tfile.read_text()).get("dram_bytes_per_cell_per_launch") * w.cells
+        try:        # ncu dram__bytes_read.sum + dram__bytes_write.sum of one depth-8 launch of the nearest captured size
+            caps = json.loads(tfile.read_text())["captures"]
+            cap = min(caps, key=lambda c: abs(np.log(c["cells"] / w.cells)))
+            traffic = cap["dram_bytes_per_cell_per_launch"] * w.cells
         except Exception:
             traffic = None
     dram_achieved = None if traffic is None or pipeline == 0 else traffic / (jac_ms / jl * 1e-3) / 1e9
