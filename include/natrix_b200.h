@@ -61,7 +61,7 @@ enum natrix_option {
                                 1 = fused / temporally blocked kernels (default)            */
     NATRIX_OPT_JACOBI_DEPTH = 1, /* sweeps per launch of the temporally blocked Jacobi kernel */
     NATRIX_OPT_TIMING = 2,   /* 1 = record per-stage CUDA events (natrix_get_timings)        */
-    NATRIX_OPT_GRAPH = 3,    /* 1 = replay natrix_step through a captured CUDA graph          */
+    NATRIX_OPT_RESERVED = 3, /* unused (kept so that the ids below stay stable)                */
     NATRIX_OPT_PACKED = 4    /* 1 = f32x2 packed arithmetic in the Jacobi kernel              */
 };
 
@@ -143,6 +143,11 @@ int natrix_dye_field_ptr(natrix_dye* dye, void** dev_ptr, size_t* bytes);
 int natrix_dye_copy_out(natrix_dye* dye, void* host, size_t bytes);
 int natrix_dye_copy_in(natrix_dye* dye, const void* host, size_t bytes);
 int natrix_dye_stats(natrix_dye* dye, double* out4);
+/* the dye buffer as the RGBA8 image the demo renders, one texel per dye cell, all four
+ * channels = the dye value converted like an rgba8 unorm imageStore: round(clamp(v, 0, 1) * 255).
+ * ref: demo/shaders/demo.ComputeShader.comp:9-21 (imageStore(InputTexture, coord, vec4(v, v, v, v))).
+ * `out` may be a device or a host pointer (is_device says which); bytes = width * height * 4. */
+int natrix_dye_export_rgba8(natrix_dye* dye, void* out, size_t bytes, int is_device);
 
 /* ---- synchronisation / introspection ------------------------------------------------- */
 int natrix_sync(natrix_sim* sim);

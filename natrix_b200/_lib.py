@@ -15,7 +15,7 @@ LIB_PATH = _PKG / "libnatrix_b200.so"
 
 # enum natrix_field / natrix_option (include/natrix_b200.h)
 VELOCITY, PRESSURE, DIVERGENCE, VORTICITY, OBSTACLES, NBMASK = range(6)
-OPT_PIPELINE, OPT_JACOBI_DEPTH, OPT_TIMING, OPT_GRAPH, OPT_PACKED = range(5)
+OPT_PIPELINE, OPT_JACOBI_DEPTH, OPT_TIMING, _OPT_RESERVED, OPT_PACKED = range(5)
 
 FIELD_COMPONENTS = {VELOCITY: 2, PRESSURE: 1, DIVERGENCE: 1, VORTICITY: 1, OBSTACLES: 2, NBMASK: 1}
 
@@ -48,6 +48,7 @@ SIGNATURES = {
     "natrix_dye_copy_out": (_i, [_vp, _vp, _sz]),
     "natrix_dye_copy_in": (_i, [_vp, _vp, _sz]),
     "natrix_dye_stats": (_i, [_vp, _pd]),
+    "natrix_dye_export_rgba8": (_i, [_vp, _vp, _sz, _i]),
     "natrix_sync": (_i, [_vp]),
     "natrix_stream": (_i, [_vp, _pvp]),
     "natrix_get_timings": (_i, [_vp, _pf, _i]),

@@ -56,7 +56,7 @@ struct natrix_sim {
     float alpha = (float)(1.0 / 0.1), rbeta = (float)(1.0 / (4.0 + 1.0 / 0.1));
     int iterations = 50, has_borders = 1, viscous = 1;
     // options
-    int pipeline = 1, jacobi_depth = 8, timing = 0, graph = 0, packed = 1;
+    int pipeline = 1, jacobi_depth = 8, timing = 0, packed = 1;
     // bookkeeping
     std::vector<SplatV> pending;                 // add_velocity calls not yet applied (pipeline 1)
     std::vector<int> heavy;                      // merged [lo, hi) local-row intervals stamped with obstacles this step
@@ -88,6 +88,7 @@ struct natrix_dye {
     int w = 0, h = 0;
     float* d[2] = {nullptr, nullptr};
     float* tables = nullptr;                    // normalised x (w floats) then y (h floats) coordinates
+    uint32_t* rgba = nullptr;                   // staging for host RGBA8 export
     int rd = 0;
     std::vector<SplatD> pending;
 };
@@ -455,7 +456,6 @@ int natrix_set_option(natrix_sim* s, int option, int value) {
         NEED(value >= 1 && value <= JACOBI_TB_MAX_DEPTH, "jacobi depth out of range");
         s->jacobi_depth = value; return 0;
     case NATRIX_OPT_TIMING: s->timing = value ? 1 : 0; return 0;
-    case NATRIX_OPT_GRAPH: s->graph = value ? 1 : 0; return 0;
     case NATRIX_OPT_PACKED: s->packed = value ? 1 : 0; return 0;
     default: return fail(NATRIX_ERR_ARG, "unknown option id");
     }
@@ -467,7 +467,6 @@ int natrix_get_option(natrix_sim* s, int option, int* value) {
     case NATRIX_OPT_PIPELINE: *value = s->pipeline; return 0;
     case NATRIX_OPT_JACOBI_DEPTH: *value = s->jacobi_depth; return 0;
     case NATRIX_OPT_TIMING: *value = s->timing; return 0;
-    case NATRIX_OPT_GRAPH: *value = s->graph; return 0;
     case NATRIX_OPT_PACKED: *value = s->packed; return 0;
     default: return fail(NATRIX_ERR_ARG, "unknown option id");
     }
@@ -705,7 +704,7 @@ int natrix_dye_destroy(natrix_dye* d) {
         auto& v = d->sim->dyes;
         for (size_t i = 0; i < v.size(); ++i) if (v[i] == d) { v.erase(v.begin() + i); break; }
     }
-    cudaFree(d->d[0]); cudaFree(d->d[1]); cudaFree(d->tables);
+    cudaFree(d->d[0]); cudaFree(d->d[1]); cudaFree(d->tables); cudaFree(d->rgba);
     delete d;
     return 0;
 }
@@ -780,6 +779,25 @@ int natrix_dye_stats(natrix_dye* d, double* out4) {
     CU(cudaMemcpyAsync(s->h_out4, s->d_out4, 4 * sizeof(double), cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
     memcpy(out4, s->h_out4, 4 * sizeof(double));
+    return 0;
+}
+
+int natrix_dye_export_rgba8(natrix_dye* d, void* out, size_t bytes, int is_device) {
+    DYE_LIVE(d);
+    const size_t n = (size_t)d->w * d->h;
+    NEED(out && bytes == n * 4, "rgba8 export expects width*height*4 bytes");
+    natrix_sim* s = d->sim;
+    if (int rc = select_device(s)) return rc;
+    if (int rc = flush_dye(d)) return rc;
+    if (is_device) {
+        s->launches += launch_dye_rgba8(d->d[d->rd], (uint32_t*)out, n, s->st);
+        CU(cudaGetLastError());
+        return 0;
+    }
+    if (!d->rgba) CU(cudaMalloc((void**)&d->rgba, n * 4));
+    s->launches += launch_dye_rgba8(d->d[d->rd], d->rgba, n, s->st);
+    CU(cudaMemcpyAsync(out, d->rgba, bytes, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
     return 0;
 }
 

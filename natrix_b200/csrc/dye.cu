@@ -106,7 +106,22 @@ k_dye_advect4(const float* __restrict__ din, float* __restrict__ dout, int pw, i
     stg_stream(reinterpret_cast<float4*>(dout + (size_t)y * pw + x0), make_float4(out[0], out[1], out[2], out[3]));
 }
 
+// ref: demo/shaders/demo.ComputeShader.comp:9-21 - the dye value replicated into the four channels of
+// an rgba8 (unorm) image: round-to-nearest of clamp(v, 0, 1) * 255 per channel.
+__global__ void __launch_bounds__(256) k_dye_rgba8(const float* __restrict__ dye, uint32_t* __restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = __float2uint_rn(clampf(dye[i], 0.0f, 1.0f) * 255.0f);
+    out[i] = c * 0x01010101u;
+}
+
 }  // namespace
+
+int launch_dye_rgba8(const float* dye, uint32_t* out, size_t n, cudaStream_t st) {
+    if (!n) return 0;
+    k_dye_rgba8<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dye, out, n);
+    return 1;
+}
 
 int launch_dye_add(const float* din, float* dout, int pw, int ph, const SplatDBatch& b, cudaStream_t st) {
     dim3 grid((pw + BX - 1) / BX, (ph + BY - 1) / BY, 1);

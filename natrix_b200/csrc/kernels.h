@@ -47,6 +47,7 @@ int launch_dye_advect(const float* din, float* dout, int pw, int ph, const float
                       const uint8_t* obs, int vw, int vh, float dt, float speed, float diss,
                       cudaStream_t st);
 
+int launch_dye_rgba8(const float* dye, uint32_t* out, size_t n, cudaStream_t st);
 // 4 cells per thread with precomputed normalised-coordinate tables (width % 4 == 0)
 int launch_dye_tables(float* nx, float* ny, int pw, int ph, int vw, int vh, cudaStream_t st);
 int launch_dye_advect4(const float* din, float* dout, int pw, int ph, const float2* vel, const uint8_t* obs,

@@ -116,6 +116,13 @@ class SmoothParticlesArea:
         arr = np.ascontiguousarray(array, dtype=np.float32).reshape(self._height, self._width)
         L.check(self._lib.natrix_dye_copy_in(self._handle(), arr.ctypes.data_as(C.c_void_p), arr.nbytes))
 
+    def export_rgba8(self) -> np.ndarray:
+        """The dye as the (H, W, 4) uint8 image the demo's compute shader writes for rendering
+        (ref: demo/shaders/demo.ComputeShader.comp:9-21)."""
+        out = np.empty((self._height, self._width, 4), np.uint8)
+        L.check(self._lib.natrix_dye_export_rgba8(self._handle(), out.ctypes.data_as(C.c_void_p), out.nbytes, 0))
+        return out
+
     def stats(self):
         out = (C.c_double * 4)()
         L.check(self._lib.natrix_dye_stats(self._handle(), out))

@@ -280,6 +280,13 @@ def advect_particles(dye, vel, obstacles, dt, speed, dissipation):
     return out.astype(F, copy=False)
 
 
+def dye_to_rgba8(dye):
+    """demo/shaders/demo.ComputeShader.comp:9-21 - imageStore of vec4(v, v, v, v) into an rgba8 (unorm)
+    image: every channel = round-to-nearest-even of clamp(v, 0, 1) * 255."""
+    c = np.rint(_clamp(dye, F(0.0), F(1.0)) * F(255.0)).astype(np.uint8)
+    return np.repeat(c[..., None], 4, axis=-1)
+
+
 # ------------------------------------------------------------------ simulator mirror
 class OracleFluidSimulator:
     """State machine of natrix/core/fluid_simulator.py:15-515 over NumPy arrays.

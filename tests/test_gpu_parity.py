@@ -320,3 +320,18 @@ def test_results_do_not_depend_on_scheduling_hints(monkeypatch):
             monkeypatch.delenv(k)
     for other in outs[1:]:
         assert_fields_close(other, outs[0], exact=True)
+
+
+def test_dye_rgba8_export_vs_oracle():
+    """the RGBA8 image of demo.ComputeShader.comp, on the device"""
+    from oracle.natrix_oracle import dye_to_rgba8
+
+    g = FluidSimulator(128, 96)
+    gd = SmoothParticlesArea(200, 150, g)
+    rng = np.random.default_rng(3)
+    dye = rng.uniform(-0.2, 1.4, (150, 200)).astype(np.float32)
+    dye[0, :5] = [0.0, 1.0, 0.5, 0.5 + 1.0 / 510.0, 2.0]
+    gd.upload(dye)
+    img = gd.export_rgba8()
+    assert img.shape == (150, 200, 4) and img.dtype == np.uint8
+    assert np.array_equal(img, dye_to_rgba8(dye))
