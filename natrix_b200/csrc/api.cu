@@ -59,6 +59,7 @@ struct natrix_sim {
     int pipeline = 1, jacobi_depth = 8, timing = 0, packed = 1;
     // bookkeeping
     std::vector<SplatV> pending;                 // add_velocity calls not yet applied (pipeline 1)
+    std::vector<float> circles;                  // queued add_circle_obstacle calls (sx, sy, r), pipeline 1
     std::vector<int> heavy;                      // merged [lo, hi) local-row intervals stamped with obstacles this step
     std::vector<int> boxes;                      // (x0, x1, y0, y1) per obstacle stamped this step (scheduling hint)
     bool obs_dirty = false, p_is_zero = false, fused_pre = false;
@@ -179,6 +180,17 @@ int flush_splats(natrix_sim* s) {
     return 0;
 }
 
+// rasterise the queued circles in one launch (pipeline 1); must run before anything reads or
+// overwrites the obstacle map
+int flush_circles(natrix_sim* s) {
+    if (s->circles.empty()) return 0;
+    s->launches += launch_add_circles(s->obs, s->g, s->ext_lo(s->g.halo), s->ext_hi(s->g.halo), s->circles.data(),
+                                      (int)s->circles.size() / 3, s->st);
+    s->circles.clear();
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int flush_dye(natrix_dye* d) {
     natrix_sim* s = d->sim;
     size_t i = 0;
@@ -216,6 +228,7 @@ int check_range_flag(natrix_sim* s) {
 int phase_advect(natrix_sim* s, float dt) {
     const Geom& g = s->g;
     if (int rc = flush_splats(s)) return rc;
+    if (int rc = flush_circles(s)) return rc;
     stamp(s, ST_ADVECT);
     const bool fold = s->pipeline != 0 && s->has_borders;
     s->fused_pre = s->pipeline != 0 && preproject_supported(g);
@@ -450,6 +463,7 @@ int natrix_set_option(natrix_sim* s, int option, int value) {
         NEED(value == 0 || value == 1, "pipeline must be 0 or 1");
         if (int rc = select_device(s)) return rc;
         if (int rc = flush_splats(s)) return rc;
+        if (int rc = flush_circles(s)) return rc;
         CU(cudaMemsetAsync(s->d_err + 1, 1, s->nbands * sizeof(int), s->st));   // pipeline 0 does not track |v| > 1
         s->pipeline = value; return 0;
     case NATRIX_OPT_JACOBI_DEPTH:
@@ -489,8 +503,13 @@ int natrix_add_circle_obstacle(natrix_sim* s, float px, float py, float radius, 
     (void)is_static;                      // both shader branches write (1,0): SURVEY Q17
     if (int rc = select_device(s)) return rc;
     const Geom& g = s->g;
-    s->launches += launch_add_circle(s->obs, g, s->ext_lo(g.halo), s->ext_hi(g.halo), px * (float)g.w,
-                                     py * (float)g.hg, radius, s->pipeline != 0, s->st);
+    if (s->pipeline != 0) {
+        // splat_pos = _Position * _Size (shader.AddCircleObstacle.comp:25), float32 products
+        s->circles.insert(s->circles.end(), {px * (float)g.w, py * (float)g.hg, radius});
+    } else {
+        s->launches += launch_add_circle(s->obs, g, s->ext_lo(g.halo), s->ext_hi(g.halo), px * (float)g.w,
+                                         py * (float)g.hg, radius, false, s->st);
+    }
     if (radius >= 0.0f)
         mark_heavy_rows(s, (double)py * g.hg - radius, (double)py * g.hg + radius, (double)px * g.w - radius,
                         (double)px * g.w + radius, true);
@@ -503,6 +522,7 @@ int natrix_add_triangle_obstacle(natrix_sim* s, float p1x, float p1y, float p2x,
                                  float p3y, int is_static) {
     NEED(s, "null simulator");
     if (int rc = select_device(s)) return rc;
+    if (int rc = flush_circles(s)) return rc;        // keep the stamping order (a static triangle stores another code)
     const Geom& g = s->g;
     s->launches += launch_add_triangle(s->obs, g, s->ext_lo(g.halo), s->ext_hi(g.halo), p1x, p1y, p2x, p2y,
                                        p3x, p3y, is_static, s->st);
@@ -596,6 +616,8 @@ int natrix_field_ptr(natrix_sim* s, int field, void** dev_ptr, size_t* bytes) {
     if (int rc = select_device(s)) return rc;
     if (field == NATRIX_VELOCITY)
         if (int rc = flush_splats(s)) return rc;
+    if (field == NATRIX_OBSTACLES)
+        if (int rc = flush_circles(s)) return rc;
     size_t elem = 0;
     if (int rc = field_info(s, field, dev_ptr, &elem)) return rc;
     if (bytes) *bytes = (size_t)s->g.w * s->g.hl * elem;
@@ -612,6 +634,7 @@ int natrix_copy_out(natrix_sim* s, int field, void* host, size_t bytes) {
     if (int rc = field_info(s, field, &src, &elem)) return rc;
     const size_t n = (size_t)s->g.w * s->g.hl;
     if (field == NATRIX_OBSTACLES) {
+        if (int rc = flush_circles(s)) return rc;
         NEED(bytes == n * sizeof(float2), "OBSTACLES copy_out expects width*height*8 bytes");
         if (!s->d_tmp2) CU(cudaMalloc((void**)&s->d_tmp2, n * sizeof(float2)));
         s->launches += launch_obs_expand(s->obs, s->d_tmp2, n, s->st);
@@ -634,6 +657,7 @@ int natrix_copy_in(natrix_sim* s, int field, const void* host, size_t bytes) {
     if (int rc = field_info(s, field, &dst, &elem)) return rc;
     const size_t n = (size_t)s->g.w * s->g.hl;
     if (field == NATRIX_OBSTACLES) {
+        if (int rc = flush_circles(s)) return rc;
         NEED(bytes == n * sizeof(float2), "OBSTACLES copy_in expects width*height*8 bytes");
         if (!s->d_tmp2) CU(cudaMalloc((void**)&s->d_tmp2, n * sizeof(float2)));
         CU(cudaMemcpyAsync(s->d_tmp2, host, bytes, cudaMemcpyHostToDevice, s->st));
@@ -727,6 +751,7 @@ int natrix_dye_step(natrix_dye* d, float dt, float speed, float dissipation) {
     natrix_sim* s = d->sim;
     if (int rc = select_device(s)) return rc;
     if (int rc = flush_splats(s)) return rc;     // the advect reads the CURRENT velocity
+    if (int rc = flush_circles(s)) return rc;    // ... and the CURRENT obstacle map
     if (int rc = flush_dye(d)) return rc;
     if (s->pipeline != 0 && d->w % 4 == 0)
         s->launches += launch_dye_advect4(d->d[d->rd], d->d[1 - d->rd], d->w, d->h, s->vel[s->vr], s->obs, s->g.w,
@@ -806,6 +831,7 @@ int natrix_sync(natrix_sim* s) {
     NEED(s, "null simulator");
     if (int rc = select_device(s)) return rc;
     if (int rc = flush_splats(s)) return rc;
+    if (int rc = flush_circles(s)) return rc;
     for (natrix_dye* d : s->dyes)
         if (int rc = flush_dye(d)) return rc;
     CU(cudaStreamSynchronize(s->st));

@@ -320,6 +320,20 @@ k_splat_dye_boxes(float* __restrict__ dye, int pw, const __grid_constant__ Splat
     dye[pos] = v;
 }
 
+// ref: shader.AddCircleObstacle.comp:24-36 for up to MAX_CIRCLES queued circles in one launch, each on
+// its own bounding box (blockIdx.z); overlapping circles store the same value.
+struct CircleBoxes { int n; float sx[MAX_CIRCLES], sy[MAX_CIRCLES], r[MAX_CIRCLES]; Box b[MAX_CIRCLES]; };
+__global__ void __launch_bounds__(SBX * SBY)
+k_add_circles(uint8_t* __restrict__ obs, const Geom g, const __grid_constant__ CircleBoxes c) {
+    const int i = blockIdx.z;
+    const Box bx = c.b[i];
+    const int x = bx.x0 + blockIdx.x * SBX + threadIdx.x;
+    const int gy = bx.y0 + blockIdx.y * SBY + threadIdx.y;
+    if (x >= bx.x1 || gy >= bx.y1) return;
+    const float ex = c.sx[i] - (float)x, ey = c.sy[i] - (float)gy;
+    if (sqrtf(ex * ex + ey * ey) <= c.r[i]) obs[lin(g, x, gy - g.y0)] = OBS_DYNAMIC;
+}
+
 // Cells with sqrt(ex^2 + ey^2) <= r lie within r + 2 of the centre along each axis (sqrt is monotone and
 // >= |ex| up to one rounding); clip to [xlo, xhi) x [ylo, yhi).  A negative or NaN radius selects nothing.
 Box splat_box(float sx, float sy, float r, int xlo, int xhi, int ylo, int yhi) {
@@ -507,6 +521,25 @@ int launch_splat_velocity_boxes(float2* vel, Geom g, int r0, int r1, const Splat
     const dim3 grid = boxes_grid(b);
     if (grid.x > 0 && grid.y > 0) {
         k_splat_velocity_boxes<<<grid, dim3(SBX, SBY, 1), 0, st>>>(vel, g, b);
+        ++launched;
+    }
+    return launched;
+}
+
+int launch_add_circles(uint8_t* obs, Geom g, int r0, int r1, const float* sxyr, int n, cudaStream_t st) {
+    int launched = 0;
+    for (int base = 0; base < n; base += MAX_CIRCLES) {
+        CircleBoxes c;
+        c.n = 0;
+        for (int i = base; i < n && c.n < MAX_CIRCLES; ++i) {
+            const Box b = splat_box(sxyr[3 * i], sxyr[3 * i + 1], sxyr[3 * i + 2], 0, g.w, g.y0 + r0, g.y0 + r1);
+            if (b.x1 <= b.x0) continue;
+            c.sx[c.n] = sxyr[3 * i]; c.sy[c.n] = sxyr[3 * i + 1]; c.r[c.n] = sxyr[3 * i + 2]; c.b[c.n] = b;
+            ++c.n;
+        }
+        const dim3 grid = boxes_grid(c);
+        if (c.n == 0 || grid.x == 0 || grid.y == 0) continue;
+        k_add_circles<<<grid, dim3(SBX, SBY, 1), 0, st>>>(obs, g, c);
         ++launched;
     }
     return launched;

@@ -10,6 +10,7 @@ namespace natrix {
 struct SplatV { float sx, sy, vx, vy, r; };       // add_velocity: splat_pos = pos * size
 struct SplatD { float sx, sy, r, value; };        // add_particles
 constexpr int MAX_SPLATS = 32;                    // per batched launch
+constexpr int MAX_CIRCLES = 64;                   // circles rasterised per launch (fused.cu)
 constexpr int OVER_BAND = 64;                     // rows per "some |v| > 1 here" flag (fused.cu)
 struct SplatVBatch { int n; SplatV s[MAX_SPLATS]; };
 struct SplatDBatch { int n; SplatD s[MAX_SPLATS]; };
@@ -71,5 +72,7 @@ int launch_zero_borders(float2* vel, Geom g, int r0, int r1, cudaStream_t st);
 int launch_splat_velocity_boxes(float2* vel, Geom g, int r0, int r1, const SplatV* splats, int n,
                                 const int* over1, int sm_count, cudaStream_t st);
 int launch_splat_dye_boxes(float* dye, int pw, int ph, const SplatD* splats, int n, cudaStream_t st);
+// n queued circles (sx, sy, radius triples, in cells) rasterised on their bounding boxes, rows [r0, r1)
+int launch_add_circles(uint8_t* obs, Geom g, int r0, int r1, const float* sxyr, int n, cudaStream_t st);
 
 }  // namespace natrix
