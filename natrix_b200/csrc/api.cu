@@ -67,6 +67,8 @@ struct natrix_sim {
                                                  // rows: some |v| > 1 in the READ velocity
     int nbands = 0;
     int* h_err = nullptr;
+    cudaEvent_t err_event = nullptr;
+    bool err_pending = false;
     int sm_count = 148;
     double *d_scratch = nullptr, *d_out4 = nullptr, *h_out4 = nullptr;
     float2* d_tmp2 = nullptr;                    // staging for OBSTACLES copy in/out
@@ -212,14 +214,29 @@ int flush_dye(natrix_dye* d) {
     return 0;
 }
 
-int check_range_flag(natrix_sim* s) {
-    // only slabs can gather outside their rows; the full grid never sets the flag
+// Slabs only (the full grid never sets the flag): did an advection back-trace leave the rows this
+// slab holds?  The flag is fetched asynchronously after every step and looked at when the copy has
+// landed - at the latest by the next step or natrix_sync - so the check never drains the stream.
+int check_range_flag(natrix_sim* s, bool wait) {
     if (s->g.hl == s->g.hg) return 0;
-    CU(cudaMemcpyAsync(s->h_err, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->st));
-    CU(cudaStreamSynchronize(s->st));
-    if (*s->h_err) {
-        CU(cudaMemsetAsync(s->d_err, 0, sizeof(int), s->st));
-        return fail(NATRIX_ERR_RANGE, "advection back-trace left the slab's halo rows; enlarge halo");
+    if (s->err_pending) {
+        if (wait) CU(cudaEventSynchronize(s->err_event));
+        const cudaError_t q = cudaEventQuery(s->err_event);
+        if (q == cudaSuccess) {
+            s->err_pending = false;
+            if (*s->h_err) {
+                *s->h_err = 0;
+                CU(cudaMemsetAsync(s->d_err, 0, sizeof(int), s->st));
+                return fail(NATRIX_ERR_RANGE, "advection back-trace left the slab's halo rows; enlarge halo");
+            }
+        } else if (q != cudaErrorNotReady) {
+            CU(q);
+        }
+    }
+    if (!s->err_pending && !wait) {
+        CU(cudaMemcpyAsync(s->h_err, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+        CU(cudaEventRecord(s->err_event, s->st));
+        s->err_pending = true;
     }
     return 0;
 }
@@ -400,6 +417,7 @@ int natrix_create_slab(int width, int global_height, int row0, int rows, int hal
     if (e == cudaSuccess) e = cudaMemsetAsync(s->d_err, 0, (1 + s->nbands) * sizeof(int), s->st);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_err, sizeof(int));
+    if (e == cudaSuccess) { *s->h_err = 0; e = cudaEventCreateWithFlags(&s->err_event, cudaEventDisableTiming); }
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_scratch, 4 * 1024 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_out4, 4 * sizeof(double));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_out4, 4 * sizeof(double));
@@ -429,6 +447,7 @@ int natrix_destroy(natrix_sim* s) {
     cudaFree(s->div_base); cudaFree(s->vort_base); cudaFree(s->obs_base); cudaFree(s->nbm_base);
     cudaFree(s->d_err); cudaFree(s->d_scratch); cudaFree(s->d_out4); cudaFree(s->d_tmp2);
     if (s->h_err) cudaFreeHost(s->h_err);
+    if (s->err_event) cudaEventDestroy(s->err_event);
     if (s->h_out4) cudaFreeHost(s->h_out4);
     for (int i = 0; i <= ST_COUNT; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     if (s->st) cudaStreamDestroy(s->st);
@@ -552,7 +571,7 @@ int natrix_step_phase(natrix_sim* s, int phase, float dt, int sweeps) {
         return phase_jacobi(s, sweeps);
     case 3: {
         if (int rc = phase_project(s)) return rc;
-        return check_range_flag(s);
+        return check_range_flag(s, false);
     }
     default: return fail(NATRIX_ERR_ARG, "phase must be 0..3");
     }
@@ -835,7 +854,8 @@ int natrix_sync(natrix_sim* s) {
     for (natrix_dye* d : s->dyes)
         if (int rc = flush_dye(d)) return rc;
     CU(cudaStreamSynchronize(s->st));
-    return 0;
+    if (int rc = check_range_flag(s, false)) return rc;      // fetch the latest flag ...
+    return check_range_flag(s, true);                        // ... and report it now
 }
 
 int natrix_stream(natrix_sim* s, void** stream) {

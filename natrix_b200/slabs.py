@@ -53,6 +53,7 @@ class CudaSlabEngine:
         self.sim = FluidSimulator(width, height, None, device=device, slab=(row0, rows, halo))
         self.device = device
         self.stream = torch.cuda.ExternalStream(self.sim.cuda_stream, device=device)
+        self._views = {}
 
     FIELD_IDS = {"velocity": 0, "pressure": 1, "divergence": 2, "nbmask": 5}
 
@@ -71,10 +72,16 @@ class CudaSlabEngine:
         return self._view(send.value, nbytes.value), self._view(recv.value, nbytes.value)
 
     def _view(self, ptr: int, nbytes: int):
-        class _Raw:
-            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
-                                        "strides": None}
-        return self.torch.as_tensor(_Raw(), device=f"cuda:{self.device}")
+        # the fields ping-pong between two buffers, so the same few (pointer, size) pairs come back every
+        # step: building a tensor view costs more host time than the exchange itself
+        key = (ptr, nbytes)
+        t = self._views.get(key)
+        if t is None:
+            class _Raw:
+                __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
+                                            "strides": None}
+            t = self._views[key] = self.torch.as_tensor(_Raw(), device=f"cuda:{self.device}")
+        return t
 
     def stream_context(self):
         return self.torch.cuda.stream(self.stream)
