@@ -251,6 +251,17 @@ def measure_single_gpu(args, w: W.Workload, with_cpu: bool, steps: int):
                         "dram_frac = traffic / launch time / peak is the physical HBM utilisation: the kernel is "
                         "instruction-issue bound, not HBM bound"}
 
+    # ---- the other stages of the step against the same roofline (algorithmic B/cell: SURVEY 8(d))
+    stage_algo = {"advect": 24 + 12 + 20 + (16 if w.viscosity > 0 else 0) + 20,   # the fused pre-projection kernel
+                  "gradient": 28}
+    stages_roofline = {}
+    if pipeline == 1:
+        for name, bpc in stage_algo.items():
+            ms = stage[name]
+            if ms > 0:
+                gbs = bpc * w.cells / (ms * 1e-3) / 1e9
+                stages_roofline[name] = {"algorithmic_bytes_per_cell": bpc, "ms": ms, "achieved": gbs, "frac": gbs / peak}
+
     # ---- CPU baseline beside it (bounded sample, all host threads)
     cpu = None
     if with_cpu and not args.no_cpu:
@@ -268,7 +279,7 @@ def measure_single_gpu(args, w: W.Workload, with_cpu: bool, steps: int):
                    "l2": "state (>= 560 MB) exceeds the 126 MB L2; no flush needed",
                    "algorithmic_GBps_full_step": step_bytes / (ms_per_step * 1e-3) / 1e9},
         "stage_ms": {k: round(v, 4) for k, v in stage.items()},
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "stages_roofline": stages_roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": METRIC, "ms_per_step": e2e_ms, "h2d_bytes_per_step": impulse_bytes_per_step(w),
                 "d2h_bytes_per_step": 32,
                 "note": "public Python API per step; inputs are the host-side impulse / obstacle parameters, the "
@@ -285,7 +296,7 @@ def run_single_gpu(args, w: W.Workload, secondary=None):
     if secondary is not None:
         # the 4096^2 configuration the metric also quotes, measured in the same run
         sub = measure_single_gpu(args, secondary, with_cpu=False, steps=max(args.steps, 20))
-        line["config3_4096"] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "config", "stage_ms", "roofline", "e2e",
+        line["config3_4096"] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "config", "stage_ms", "roofline", "stages_roofline", "e2e",
                                                      "gpu_launches")}
     print(json.dumps(line), flush=True)
     return 0

@@ -335,3 +335,20 @@ def test_dye_rgba8_export_vs_oracle():
     img = gd.export_rgba8()
     assert img.shape == (150, 200, 4) and img.dtype == np.uint8
     assert np.array_equal(img, dye_to_rgba8(dye))
+
+
+def test_config5_slab_size_fused_equals_reference_order_pipeline():
+    """config 5 at its per-GPU size (32768 x 4096, 64 circles): tile planner, select / solid / free bodies
+    and the fused pre-projection against the one-kernel-per-shader pipeline, bit for bit (24 sweeps)."""
+    w = W.cfg5_workload(1)
+    w.iterations = 24
+    a, _ = W.build(w, _sim_cls(0), None)
+    b, _ = W.build(w, _sim_cls(1), None)
+    for k in range(2):
+        W.run_step(w, a, None, k)
+        W.run_step(w, b, None, k)
+    for name in ("velocity", "pressure", "divergence", "vorticity"):
+        fa, fb = a.download(name), b.download(name)
+        assert np.array_equal(fa, fb), f"{name}: {int(np.count_nonzero(fa != fb))} cells differ"
+        assert float(np.abs(fa).max()) > 0.0
+        del fa, fb
