@@ -6,8 +6,8 @@ local stencil or a bounded gather, so the only data-path communication is a poin
 exchange of halo rows with the two neighbouring ranks (NCCL send/recv over NVLink):
 
     before advect                 velocity     ceil(1.25 dt speed) + 5 rows
-    after divergence              divergence, blocked-neighbour mask     T rows   (T = Jacobi depth)
-    before every Jacobi block     pressure     T rows   (not the first: p starts at zero)
+    after divergence              divergence, blocked-neighbour mask     k T rows   (T = Jacobi depth)
+    before every k Jacobi blocks  pressure     k T rows, k = halo // T   (not the first: p starts at zero)
     before gradient subtraction   pressure     1 row
 
 Obstacles and impulses are functions of global cell coordinates: every rank rasterises its own
@@ -162,12 +162,15 @@ class SlabSimulator:
         self.exchange("velocity", e.rows_needed(0, time_delta))
         e.phase(0, time_delta)
         e.phase(1, time_delta)
+        # Several Jacobi launches per exchange: with k * depth halo rows the slab recomputes the rows its
+        # neighbour owns for the first k - 1 launches (a few rows) instead of exchanging after every one.
+        span = max(1, self.halo // self.depth) * self.depth
         left, first = int(self.iterations), True
         while left > 0:
-            t = min(self.depth, left)
+            t = min(span, left)
             if first:
-                self.exchange("divergence", self.depth)
-                self.exchange("nbmask", self.depth)
+                self.exchange("divergence", min(span, int(self.iterations)))
+                self.exchange("nbmask", min(span, int(self.iterations)))
             else:
                 self.exchange("pressure", t)
             e.phase(2, time_delta, t)

@@ -22,7 +22,7 @@ sys.path.insert(0, str(ROOT))
 from natrix_b200.slabs import SlabSimulator, partition_rows  # noqa: E402
 from oracle import natrix_oracle as O  # noqa: E402
 
-W, H, ITER, DEPTH, HALO = 48, 61, 19, 4, 6
+W, H, ITER, DEPTH, HALO = 48, 61, 19, 4, 9        # halo 9: two Jacobi blocks (8 sweeps) per pressure exchange
 
 
 def test_partition_rows_covers_the_grid():
@@ -115,8 +115,9 @@ def _worker(rank, world, port, errors):
         assert np.array_equal(eng.own(eng.div), div[row0:row0 + rows]), "divergence"
         assert np.array_equal(eng.own(eng.p), p[row0:row0 + rows]), "pressure"
         assert np.array_equal(eng.own(eng.vel), out[row0:row0 + rows]), "velocity"
-        # schedule: velocity, divergence, mask, ceil(N/T)-1 pressure blocks, final pressure row
-        assert slab.exchanges == 3 + (-(-ITER // DEPTH) - 1) + 1, slab.exchanges
+        # schedule: velocity, divergence, mask, ceil(N / span) - 1 pressure exchanges, final pressure row
+        span = (HALO // DEPTH) * DEPTH
+        assert slab.exchanges == 3 + (-(-ITER // span) - 1) + 1, slab.exchanges
         with pytest.raises(ValueError):
             slab.exchange("pressure", HALO + 1)
         dist.barrier()
