@@ -110,6 +110,9 @@ cudaError_t alloc_rows(T** base, T** view, const natrix_sim* s) {
 // remember which rows carry obstacles (scheduling hint for the Jacobi kernel); keeps the list merged
 void mark_heavy_rows(natrix_sim* s, double glo, double ghi, double xlo = -1e30, double xhi = 1e30, bool circle = false) {
     const int margin = 2;
+    const int by0 = std::max((int)std::floor(std::max(glo, -1e9)) - margin - s->g.y0, -s->g.halo);
+    const int by1 = std::min((int)std::ceil(std::min(ghi, 1e9)) + margin + 1 - s->g.y0, s->g.hl + s->g.halo);
+    if (by1 <= by0) return;                          // does not touch the rows this slab holds
     if (circle && s->boxes.size() < 4 * 256) {
         // a circle keeps its geometry: (cx, -1 - r, cy local, 0), see jacobi_tb.h
         const double r = 0.5 * (ghi - glo);
@@ -117,9 +120,7 @@ void mark_heavy_rows(natrix_sim* s, double glo, double ghi, double xlo = -1e30, 
                                          (int)std::lround(0.5 * (glo + ghi)) - s->g.y0, 0});
     } else {
         const int bx0 = (int)std::max(0.0, std::floor(xlo) - margin), bx1 = (int)std::min((double)s->g.w, std::ceil(xhi) + margin + 1);
-        const int by0 = std::max((int)std::floor(std::max(glo, -1e9)) - margin - s->g.y0, -s->g.halo);
-        const int by1 = std::min((int)std::ceil(std::min(ghi, 1e9)) + margin + 1 - s->g.y0, s->g.hl + s->g.halo);
-        if (bx1 > bx0 && by1 > by0) {
+        if (bx1 > bx0) {
             if (s->boxes.size() >= 4 * 256) {        // too many to plan around: one box over everything
                 s->boxes = {0, s->g.w, -s->g.halo, s->g.hl + s->g.halo};
             } else {

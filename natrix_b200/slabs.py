@@ -6,7 +6,7 @@ local stencil or a bounded gather, so the only data-path communication is a poin
 exchange of halo rows with the two neighbouring ranks (NCCL send/recv over NVLink):
 
     before advect                 velocity     ceil(1.25 dt speed) + 5 rows
-    after divergence              divergence, blocked-neighbour mask     k T rows   (T = Jacobi depth)
+    after divergence              divergence + blocked-neighbour mask (one batch)   k T rows   (T = Jacobi depth)
     before every k Jacobi blocks  pressure     k T rows, k = halo // T   (not the first: p starts at zero)
     before gradient subtraction   pressure     1 row
 
@@ -131,24 +131,24 @@ class SlabSimulator:
             self.sim.add_triangle_obstacle(p1, p2, p3, static)
 
     # -- halo exchange with the two neighbouring ranks
-    def exchange(self, field: str, rows: int):
+    def exchange(self, fields, rows: int):
+        """Swap `rows` halo rows of one field (or of several, in one batched NCCL group) with both neighbours."""
+        if isinstance(fields, str):
+            fields = (fields,)
         if rows <= 0 or self.world == 1:
             return
         if rows > self.halo:
-            raise ValueError(f"{field}: step needs {rows} halo rows but the slab was created with {self.halo}")
+            raise ValueError(f"{'+'.join(fields)}: step needs {rows} halo rows but the slab was created with {self.halo}")
         dist = self.dist
         ops, keep = [], []
-        up, down = self.rank - 1, self.rank + 1
-        ctx = self.engine.stream_context()
-        with ctx:
-            if up >= 0:
-                send, recv = self.engine.halo_region(field, 0, rows)
-                ops += [dist.P2POp(dist.isend, send, up, self.group), dist.P2POp(dist.irecv, recv, up, self.group)]
-                keep += [send, recv]
-            if down < self.world:
-                send, recv = self.engine.halo_region(field, 1, rows)
-                ops += [dist.P2POp(dist.isend, send, down, self.group), dist.P2POp(dist.irecv, recv, down, self.group)]
-                keep += [send, recv]
+        with self.engine.stream_context():
+            for peer, side in ((self.rank - 1, 0), (self.rank + 1, 1)):
+                if peer < 0 or peer >= self.world:
+                    continue
+                for field in fields:
+                    send, recv = self.engine.halo_region(field, side, rows)
+                    ops += [dist.P2POp(dist.isend, send, peer, self.group), dist.P2POp(dist.irecv, recv, peer, self.group)]
+                    keep += [send, recv]
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
         self.exchanges += 1
@@ -169,8 +169,7 @@ class SlabSimulator:
         while left > 0:
             t = min(span, left)
             if first:
-                self.exchange("divergence", min(span, int(self.iterations)))
-                self.exchange("nbmask", min(span, int(self.iterations)))
+                self.exchange(("divergence", "nbmask"), min(span, int(self.iterations)))
             else:
                 self.exchange("pressure", t)
             e.phase(2, time_delta, t)
@@ -229,8 +228,10 @@ def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
     dist.barrier()
     torch.cuda.synchronize()
     ev0.record(stream)
+    h0 = time.perf_counter()
     for _ in range(args.steps):
         one_step(step); step += 1
+    host_ms = 1e3 * (time.perf_counter() - h0) / args.steps      # host time to enqueue one step (not a result)
     sim.synchronize()
     ev1.record(stream)
     torch.cuda.synchronize()
@@ -294,7 +295,8 @@ def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
             "weak_base": {"workload": w1.name, "n_gpus": 1, "value": base_value, "ms_per_step": float(bms.item()),
                           "note": "same per-GPU slab run standalone on every rank of this box (max over ranks)"},
             "halo": {"exchanges_per_step": slab.exchanges / (3 * args.steps + max(args.warmup, 3)),
-                     "bytes_per_step_per_neighbour": slab.exchanged_bytes / max(slab.exchanges, 1)},
+                     "bytes_per_exchange_per_neighbour": slab.exchanged_bytes / max(slab.exchanges, 1),
+                     "host_enqueue_ms_per_step": host_ms},
             "e2e": {"value": w.cells / (float(e2e_ms.item()) * 1e-3) / 1e6, "unit": metric,
                     "ms_per_step": float(e2e_ms.item()), "h2d_bytes_per_step": 16 * len(w.circles) + 32,
                     "d2h_bytes_per_step": 32},

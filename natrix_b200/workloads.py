@@ -79,11 +79,15 @@ def cfg4_workload(size: int = 16384) -> Workload:
 
 
 def cfg5_workload(n_gpus: int = 1, width: int = 32768, rows_per_gpu: int = 4096) -> Workload:
-    """config 5 - 32768^2 weak scaling: 32768 x 4096 per GPU, 200 iterations, 64 circles."""
+    """config 5 - 32768^2 weak scaling: 32768 x 4096 cells, 200 iterations and 64 circles PER GPU.
+
+    The N-GPU domain is the 1-GPU domain tiled N times along y (the same 64 circles in every 4096-row band),
+    so the work per GPU - obstacle load included - does not change with N."""
     height = rows_per_gpu * n_gpus
     rng = np.random.default_rng(2)
-    circles = [(float(rng.uniform(0.05, 0.95)), float(rng.uniform(0.05, 0.95)), float(rng.uniform(64.0, 512.0)))
-               for _ in range(64)]
+    band = [(float(rng.uniform(0.05, 0.95)), float(rng.uniform(0.05, 0.95)), float(rng.uniform(64.0, 512.0)))
+            for _ in range(64)]
+    circles = [(x, (g + y) / n_gpus, r) for g in range(n_gpus) for (x, y, r) in band]
     return Workload(f"{width}x{height}-N200-weak", width, height, 200, 1.0, 0.0, circles=circles, init="smooth")
 
 
