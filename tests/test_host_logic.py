@@ -54,7 +54,7 @@ def test_workloads_are_deterministic_and_match_baseline_configs():
     assert (w1.width, w1.height, w1.iterations, w1.viscosity, w1.dye_size) == (640, 360, 50, 0.5, (1280, 720))
     assert W.cfg2_workload().algorithmic_bytes_per_cell_step() == 132 + 20 * 50
     w5 = W.cfg5_workload(8)
-    assert (w5.width, w5.height, w5.iterations, len(w5.circles)) == (32768, 32768, 200, 64)
+    assert (w5.width, w5.height, w5.iterations, len(w5.circles)) == (32768, 32768, 200, 64 * 8)   # 64 per GPU band
 
 
 def test_smooth_velocity_slab_equals_window_of_full_field():
