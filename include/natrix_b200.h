@@ -109,7 +109,13 @@ int natrix_step(natrix_sim* sim, float dt);
  *   0 advect (needs VELOCITY halo of natrix_halo_rows_needed(sim, 0, dt) rows)
  *   1 vorticity+confinement(+viscosity)+divergence+mask (needs post-advect VELOCITY halo 4)
  *   2 `sweeps` Jacobi sweeps (needs PRESSURE halo `sweeps`, DIVERGENCE+NBMASK halo `sweeps`)
- *   3 subtract gradient + clear obstacles (needs PRESSURE halo 1)                         */
+ *   3 subtract gradient + clear obstacles (needs PRESSURE halo 1)
+ * Overlapped form of phase 2, for a group of `sweeps` <= halo sweeps between two exchanges:
+ *   4 starts the group's interior rows (they need no halo) on the simulator's stream and returns;
+ *   5 runs the group's edge rows on the stream natrix_comm_stream returns - where the host has queued
+ *     the PRESSURE (first group of a step: DIVERGENCE + NBMASK) exchange of `sweeps` rows between the
+ *     two calls - and the rest of the interior on the simulator's stream, which finally waits for the
+ *     edges.  4 and 5 come in pairs with the same `sweeps`; the slab needs >= 2 * sweeps rows. */
 int natrix_step_phase(natrix_sim* sim, int phase, float dt, int sweeps);
 int natrix_halo_rows_needed(natrix_sim* sim, int phase, float dt);
 /* Device addresses of the rows to send / to receive for one field:
@@ -153,6 +159,9 @@ int natrix_dye_export_rgba8(natrix_dye* dye, void* out, size_t bytes, int is_dev
 int natrix_sync(natrix_sim* sim);
 /* CUDA stream the simulator enqueues on (a cudaStream_t), for event timing by the caller. */
 int natrix_stream(natrix_sim* sim, void** stream);
+/* Second, high-priority stream of a slab handle: halo exchanges queued here overlap the interior
+ * Jacobi launches of natrix_step_phase(sim, 4, ..) (see above). */
+int natrix_comm_stream(natrix_sim* sim, void** stream);
 /* Per-stage milliseconds of the last step when NATRIX_OPT_TIMING is on.  Index:
  * 0 advect, 1 vorticity/confinement/viscosity, 2 divergence, 3 jacobi, 4 gradient, 5 clears. */
 int natrix_get_timings(natrix_sim* sim, float* ms, int n);

@@ -51,6 +51,7 @@ SIGNATURES = {
     "natrix_dye_export_rgba8": (_i, [_vp, _vp, _sz, _i]),
     "natrix_sync": (_i, [_vp]),
     "natrix_stream": (_i, [_vp, _pvp]),
+    "natrix_comm_stream": (_i, [_vp, _pvp]),
     "natrix_get_timings": (_i, [_vp, _pf, _i]),
     "natrix_launch_count": (_i, [_vp, C.POINTER(C.c_ulonglong)]),
     "natrix_last_error": (C.c_char_p, []),

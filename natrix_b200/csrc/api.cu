@@ -77,6 +77,12 @@ struct natrix_sim {
     float stage_ms[ST_COUNT] = {};
     JacobiTB* tb = nullptr;
     std::vector<natrix_dye*> dyes;
+    // slabs, overlapped halo exchange: the exchange and the edge zones of a Jacobi group run on st_edge
+    // while the interior runs on st (phase_jacobi_interior / phase_jacobi_edges)
+    cudaStream_t st_edge = nullptr;
+    cudaEvent_t ev_group = nullptr, ev_edges = nullptr, ev_xchg = nullptr;
+    std::vector<cudaEvent_t> ev_int;             // after the j-th interior launch of the open group
+    int group_open = 0;                          // sweeps of the group whose interior is queued, else 0
 
     int ext_lo(int k) const { int lo = -k; if (g.y0 + lo < 0) lo = -g.y0; return lo < -g.halo ? -g.halo : lo; }
     int ext_hi(int k) const {
@@ -306,33 +312,134 @@ int phase_forces(natrix_sim* s, float dt) {
 }
 
 // `sweeps` Jacobi sweeps; requires p, div, nbmask valid on ext(sweeps) (exchange done by caller)
-int phase_jacobi(natrix_sim* s, int sweeps) {
+// One launch of `depth` Jacobi sweeps over local rows [r0, r1): p[src] -> p[1 - src] on stream st.
+int jacobi_rows(natrix_sim* s, int src, int depth, int r0, int r1, bool p_zero, cudaStream_t st) {
+    if (r1 <= r0) return 0;
     const Geom& g = s->g;
+    if (s->pipeline == 0) {
+        s->launches += launch_poisson_ref(s->p[src], s->div, s->obs, s->p[1 - src], g, r0, r1, st);
+    } else if (!jacobi_tb_supported(g)) {
+        // widths TMA cannot address (not a multiple of 16, or narrower than one strip)
+        s->launches += launch_poisson_mask(s->p[src], s->div, s->nbm, s->p[1 - src], g, r0, r1, st);
+    } else {
+        int n = jacobi_tb_launch(s->tb, s->p[src], s->div, s->nbm, s->p[1 - src], g, depth, r0, r1, p_zero, s->packed,
+                                 s->boxes.data(), (int)s->boxes.size() / 4, st);
+        if (n < 0) return fail(NATRIX_ERR_CUDA, std::string("jacobi_tb: ") + jacobi_tb_error(s->tb));
+        s->launches += n;
+    }
+    return 0;
+}
+
+int jacobi_launch_depth(const natrix_sim* s) {
+    return (s->pipeline == 0 || !jacobi_tb_supported(s->g)) ? 1 : s->jacobi_depth;
+}
+
+int phase_jacobi(natrix_sim* s, int sweeps) {
     int left = sweeps;
     while (left > 0) {
-        if (s->pipeline == 0) {
-            s->launches += launch_poisson_ref(s->p[s->pr], s->div, s->obs, s->p[1 - s->pr], g,
-                                              s->ext_lo(left - 1), s->ext_hi(left - 1), s->st);
-            s->pr = 1 - s->pr;
-            left -= 1;
-        } else if (!jacobi_tb_supported(g)) {
-            // widths TMA cannot address (not a multiple of 16, or narrower than one strip)
-            s->launches += launch_poisson_mask(s->p[s->pr], s->div, s->nbm, s->p[1 - s->pr], g,
-                                               s->ext_lo(left - 1), s->ext_hi(left - 1), s->st);
-            s->pr = 1 - s->pr;
-            left -= 1;
-        } else {
-            int t = left < s->jacobi_depth ? left : s->jacobi_depth;
-            int n = jacobi_tb_launch(s->tb, s->p[s->pr], s->div, s->nbm, s->p[1 - s->pr], g, t,
-                                     s->ext_lo(left - t), s->ext_hi(left - t), s->p_is_zero, s->packed,
-                                     s->boxes.data(), (int)s->boxes.size() / 4, s->st);
-            if (n < 0) return fail(NATRIX_ERR_CUDA, std::string("jacobi_tb: ") + jacobi_tb_error(s->tb));
-            s->launches += n;
-            s->pr = 1 - s->pr;
-            left -= t;
-        }
+        const int t = std::min(left, jacobi_launch_depth(s));
+        if (int rc = jacobi_rows(s, s->pr, t, s->ext_lo(left - t), s->ext_hi(left - t), s->p_is_zero, s->st)) return rc;
+        s->pr = 1 - s->pr;
+        left -= t;
         s->p_is_zero = false;
     }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ---- overlapped halo exchange (slabs) ----------------------------------------------------------------
+// A group of `sweeps` Jacobi sweeps between two pressure exchanges is cut by rows.  The interior - the rows
+// whose value after the group depends on no halo row - runs on the main stream, the edge zones on st_edge
+// behind the exchange the host issues there:
+//
+//   launch j (depth d_j, c_j = d_1 + .. + d_j):  interior [c_j, hl - c_j)        p[src] -> p[1 - src]
+//                                                 edges    [ext_lo(sweeps - c_j), c_j) and the mirror image
+//
+//   main    | I_1 ............ | wait X | I_2 ...... | I_3 ...... |           | wait E | next group
+//   st_edge | exchange X | B_1 |          wait I_1 | B_2 | wait I_2 | B_3 | E
+//
+// I_1 overlaps the exchange.  I_2 writes the buffer the exchange sends from, so it waits for X; from there
+// on the edge launch j only needs the interior launch j - 1 (its rows [c_{j-1}, c_j + d_j) come from there).
+// Launch depths never decrease inside a group (a partial launch goes first), so edge launch j, which reads
+// rows below c_j + d_j of its source, and interior launch j + 1, which writes rows from c_{j+1} of the same
+// buffer, never touch the same row.  The next group's interior waits for this group's edges (E).
+std::vector<int> group_depths(int sweeps, int depth) {
+    std::vector<int> d;
+    if (sweeps % depth) d.push_back(sweeps % depth);
+    for (int k = 0; k < sweeps / depth; ++k) d.push_back(depth);
+    return d;
+}
+
+int ensure_edge_stream(natrix_sim* s) {
+    if (s->st_edge) return 0;
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    // highest priority: edge blocks are few and the next exchange waits for them
+    CU(cudaStreamCreateWithPriority(&s->st_edge, cudaStreamNonBlocking, hi));
+    CU(cudaEventCreateWithFlags(&s->ev_group, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s->ev_edges, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s->ev_xchg, cudaEventDisableTiming));
+    return 0;
+}
+
+int interior_launch(natrix_sim* s, const std::vector<int>& depths, size_t j, int src, int done) {
+    const Geom& g = s->g;
+    const bool up = g.y0 > 0, down = g.y0 + g.hl < g.hg;
+    if (int rc = jacobi_rows(s, src, depths[j], up ? done : 0, down ? g.hl - done : g.hl, s->p_is_zero && j == 0, s->st))
+        return rc;
+    CU(cudaEventRecord(s->ev_int[j], s->st));
+    return 0;
+}
+
+// phase 4: the first interior launch of the group; the host queues the exchange on st_edge next
+int phase_jacobi_interior(natrix_sim* s, int sweeps) {
+    const Geom& g = s->g;
+    const bool up = g.y0 > 0, down = g.y0 + g.hl < g.hg;
+    if (s->group_open) return fail(NATRIX_ERR_STATE, "a Jacobi group is open: call phase 5 first");
+    if ((up || down) && sweeps > g.halo) return fail(NATRIX_ERR_ARG, "group is deeper than the slab's halo");
+    if (g.hl < 2 * sweeps) return fail(NATRIX_ERR_STATE, "slab is too short to split into interior and edges");
+    if (int rc = ensure_edge_stream(s)) return rc;
+    // everything queued so far (divergence, the previous group) precedes the exchange and the edge zones
+    CU(cudaEventRecord(s->ev_group, s->st));
+    CU(cudaStreamWaitEvent(s->st_edge, s->ev_group, 0));
+    const std::vector<int> depths = group_depths(sweeps, jacobi_launch_depth(s));
+    while (s->ev_int.size() < depths.size()) {
+        cudaEvent_t e = nullptr;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s->ev_int.push_back(e);
+    }
+    if (int rc = interior_launch(s, depths, 0, s->pr, depths[0])) return rc;
+    s->group_open = sweeps;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// phase 5: the exchange is queued on st_edge; edge launches there, the remaining interior launches on main
+int phase_jacobi_edges(natrix_sim* s, int sweeps) {
+    const Geom& g = s->g;
+    const bool up = g.y0 > 0, down = g.y0 + g.hl < g.hg;
+    if (s->group_open != sweeps) return fail(NATRIX_ERR_STATE, "phase 5 must follow phase 4 with the same sweeps");
+    const std::vector<int> depths = group_depths(sweeps, jacobi_launch_depth(s));
+    CU(cudaEventRecord(s->ev_xchg, s->st_edge));
+    CU(cudaStreamWaitEvent(s->st, s->ev_xchg, 0));
+    int src = s->pr, done = 0;
+    for (size_t j = 0; j < depths.size(); ++j) {
+        if (j > 0) CU(cudaStreamWaitEvent(s->st_edge, s->ev_int[j - 1], 0));
+        done += depths[j];
+        const bool pz = s->p_is_zero && j == 0;
+        if (up)
+            if (int rc = jacobi_rows(s, src, depths[j], s->ext_lo(sweeps - done), done, pz, s->st_edge)) return rc;
+        if (down)
+            if (int rc = jacobi_rows(s, src, depths[j], g.hl - done, s->ext_hi(sweeps - done), pz, s->st_edge)) return rc;
+        src = 1 - src;
+        if (j + 1 < depths.size())
+            if (int rc = interior_launch(s, depths, j + 1, src, done + depths[j + 1])) return rc;
+    }
+    CU(cudaEventRecord(s->ev_edges, s->st_edge));
+    CU(cudaStreamWaitEvent(s->st, s->ev_edges, 0));
+    s->pr = src;
+    s->p_is_zero = false;
+    s->group_open = 0;
     CU(cudaGetLastError());
     return 0;
 }
@@ -451,6 +558,11 @@ int natrix_destroy(natrix_sim* s) {
     if (s->err_event) cudaEventDestroy(s->err_event);
     if (s->h_out4) cudaFreeHost(s->h_out4);
     for (int i = 0; i <= ST_COUNT; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->st_edge) { cudaStreamSynchronize(s->st_edge); cudaStreamDestroy(s->st_edge); }
+    if (s->ev_group) cudaEventDestroy(s->ev_group);
+    if (s->ev_edges) cudaEventDestroy(s->ev_edges);
+    if (s->ev_xchg) cudaEventDestroy(s->ev_xchg);
+    for (cudaEvent_t e : s->ev_int) cudaEventDestroy(e);
     if (s->st) cudaStreamDestroy(s->st);
     delete s;
     return 0;
@@ -574,7 +686,12 @@ int natrix_step_phase(natrix_sim* s, int phase, float dt, int sweeps) {
         if (int rc = phase_project(s)) return rc;
         return check_range_flag(s, false);
     }
-    default: return fail(NATRIX_ERR_ARG, "phase must be 0..3");
+    case 4:
+        NEED(sweeps > 0, "sweeps must be positive");
+        if (s->p_is_zero) stamp(s, ST_JACOBI);
+        return phase_jacobi_interior(s, sweeps);
+    case 5: return phase_jacobi_edges(s, sweeps);
+    default: return fail(NATRIX_ERR_ARG, "phase must be 0..5");
     }
 }
 
@@ -862,6 +979,14 @@ int natrix_sync(natrix_sim* s) {
 int natrix_stream(natrix_sim* s, void** stream) {
     NEED(s && stream, "null argument");
     *stream = (void*)s->st;
+    return 0;
+}
+
+int natrix_comm_stream(natrix_sim* s, void** stream) {
+    NEED(s && stream, "null argument");
+    if (int rc = select_device(s)) return rc;
+    if (int rc = ensure_edge_stream(s)) return rc;
+    *stream = (void*)s->st_edge;
     return 0;
 }
 

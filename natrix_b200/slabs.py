@@ -10,6 +10,10 @@ exchange of halo rows with the two neighbouring ranks (NCCL send/recv over NVLin
     before every k Jacobi blocks  pressure     k T rows, k = halo // T   (not the first: p starts at zero)
     before gradient subtraction   pressure     1 row
 
+The exchanges inside the Jacobi phase are overlapped with compute: the interior rows of a group of k
+blocks need no halo and start at once on the simulator's stream (natrix_step_phase 4) while the exchange
+and then the few edge rows (phase 5) run on a second, high-priority stream.
+
 Obstacles and impulses are functions of global cell coordinates: every rank rasterises its own
 rows (halo rows included), no exchange.  Halo rows are recomputed redundantly from the same
 inputs in the same order, so the result is bit-identical to the single-GPU run.
@@ -53,7 +57,12 @@ class CudaSlabEngine:
         self.sim = FluidSimulator(width, height, None, device=device, slab=(row0, rows, halo))
         self.device = device
         self.stream = torch.cuda.ExternalStream(self.sim.cuda_stream, device=device)
+        comm = C.c_void_p()
+        L.check(self.sim._lib.natrix_comm_stream(self.sim._handle(), C.byref(comm)))
+        self.comm_stream = torch.cuda.ExternalStream(comm.value, device=device)
         self._views = {}
+
+    supports_overlap = True          # natrix_step_phase 4 / 5 (interior / edges of a Jacobi group)
 
     FIELD_IDS = {"velocity": 0, "pressure": 1, "divergence": 2, "nbmask": 5}
 
@@ -83,15 +92,15 @@ class CudaSlabEngine:
             t = self._views[key] = self.torch.as_tensor(_Raw(), device=f"cuda:{self.device}")
         return t
 
-    def stream_context(self):
-        return self.torch.cuda.stream(self.stream)
+    def stream_context(self, comm: bool = False):
+        return self.torch.cuda.stream(self.comm_stream if comm else self.stream)
 
 
 class SlabSimulator:
     """The reference's FluidSimulator surface for one rank's slab of a global grid."""
 
     def __init__(self, width: int, height: int, engine=None, halo: int = DEFAULT_HALO, device: Optional[int] = None,
-                 group=None, depth: int = 8):
+                 group=None, depth: int = 8, overlap: Optional[bool] = None):
         import torch.distributed as dist
 
         self.dist = dist
@@ -108,6 +117,11 @@ class SlabSimulator:
             engine = CudaSlabEngine(self.width, self.height, self.row0, self.rows, self.halo, dev)
         self.engine = engine
         self.depth = int(depth)
+        # overlap the pressure exchanges with the interior Jacobi launches when the engine can split a group
+        can = bool(getattr(engine, "supports_overlap", False))
+        if overlap is None:
+            overlap = os.environ.get("NATRIX_SLAB_OVERLAP", "1") != "0"      # A/B switch for measurements
+        self.overlap = bool(overlap) and can
         self.iterations = 50
         self.simulate = True
         self.exchanges = 0
@@ -131,8 +145,9 @@ class SlabSimulator:
             self.sim.add_triangle_obstacle(p1, p2, p3, static)
 
     # -- halo exchange with the two neighbouring ranks
-    def exchange(self, fields, rows: int):
-        """Swap `rows` halo rows of one field (or of several, in one batched NCCL group) with both neighbours."""
+    def exchange(self, fields, rows: int, comm: bool = False):
+        """Swap `rows` halo rows of one field (or of several, in one batched NCCL group) with both neighbours,
+        on the simulator's stream or (comm=True) on its second stream."""
         if isinstance(fields, str):
             fields = (fields,)
         if rows <= 0 or self.world == 1:
@@ -141,7 +156,7 @@ class SlabSimulator:
             raise ValueError(f"{'+'.join(fields)}: step needs {rows} halo rows but the slab was created with {self.halo}")
         dist = self.dist
         ops, keep = [], []
-        with self.engine.stream_context():
+        with (self.engine.stream_context(True) if comm else self.engine.stream_context()):
             for peer, side in ((self.rank - 1, 0), (self.rank + 1, 1)):
                 if peer < 0 or peer >= self.world:
                     continue
@@ -164,17 +179,19 @@ class SlabSimulator:
         e.phase(1, time_delta)
         # Several Jacobi launches per exchange: with k * depth halo rows the slab recomputes the rows its
         # neighbour owns for the first k - 1 launches (a few rows) instead of exchanging after every one.
+        # A partial group goes first so that launch depths never decrease (natrix_step_phase 4 / 5).
+        n = int(self.iterations)
         span = max(1, self.halo // self.depth) * self.depth
-        left, first = int(self.iterations), True
-        while left > 0:
-            t = min(span, left)
-            if first:
-                self.exchange(("divergence", "nbmask"), min(span, int(self.iterations)))
+        groups = ([n % span] if n % span else []) + [span] * (n // span)
+        overlap = self.overlap and self.world > 1 and self.rows >= 2 * span
+        for i, t in enumerate(groups):
+            if overlap:
+                e.phase(4, time_delta, t)                     # interior rows: no halo needed
+            if i == 0:
+                self.exchange(("divergence", "nbmask"), min(span, n), comm=overlap)
             else:
-                self.exchange("pressure", t)
-            e.phase(2, time_delta, t)
-            left -= t
-            first = False
+                self.exchange("pressure", t, comm=overlap)
+            e.phase(5 if overlap else 2, time_delta, t)       # edge rows (or all rows) after the exchange
         self.exchange("pressure", 1)
         e.phase(3, time_delta)
 
@@ -289,7 +306,8 @@ def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w.name, "grid": [w.width, w.height], "per_gpu_grid": [w.width, slab.rows],
                        "jacobi_iterations": w.iterations, "obstacles_per_step": len(w.circles),
-                       "parallelism": f"row-slabs x{world}, halo {slab.halo} rows, NCCL send/recv",
+                       "parallelism": f"row-slabs x{world}, halo {slab.halo} rows, NCCL send/recv"
+                                      + (", pressure exchanges overlapped with interior Jacobi" if slab.overlap else ""),
                        "jacobi_depth": depth, "l2": "per-GPU state 4.6 GB exceeds L2; no flush needed",
                        "algorithmic_GBps_per_gpu": algo / world / (ms_per_step * 1e-3) / 1e9},
             "weak_base": {"workload": w1.name, "n_gpus": 1, "value": base_value, "ms_per_step": float(bms.item()),

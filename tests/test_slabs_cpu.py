@@ -37,7 +37,9 @@ class NumpySlabEngine:
     """Slab of the projection half of the step (divergence -> N Jacobi sweeps -> gradient) on arrays
     with `halo` extra rows where a neighbour exists."""
 
-    def __init__(self, vel, obs, row0, rows, halo, height):
+    def __init__(self, vel, obs, row0, rows, halo, height, overlap=False):
+        self.supports_overlap = overlap
+        self._interior = None
         self.row0, self.rows, self.height = row0, rows, height
         self.top = halo if row0 > 0 else 0                    # halo rows actually present above / below
         self.bot = halo if row0 + rows < height else 0
@@ -54,7 +56,7 @@ class NumpySlabEngine:
     def rows_needed(self, phase, dt):
         return {0: 1, 1: 0, 2: DEPTH, 3: 1}[phase]
 
-    def stream_context(self):
+    def stream_context(self, comm=False):
         import contextlib
         return contextlib.nullcontext()
 
@@ -80,6 +82,21 @@ class NumpySlabEngine:
         elif phase == 2:
             for _ in range(sweeps):
                 self.p = O.poisson_sweep(self.p, self.div, self.obs)
+        elif phase == 4:
+            # interior of a group, BEFORE the exchange: rows at least `sweeps` away from a neighbour's rows
+            assert self._interior is None
+            q = self.p.copy()
+            for _ in range(sweeps):
+                q = O.poisson_sweep(q, self.div, self.obs)
+            lo = self.top + (sweeps if self.top else 0)
+            hi = self.top + self.rows - (sweeps if self.bot else 0)
+            self._interior = (sweeps, lo, hi, q[lo:hi].copy())
+        elif phase == 5:
+            t, lo, hi, rows = self._interior
+            assert t == sweeps
+            self._interior = None
+            self.phase(2, dt, sweeps)                        # after the exchange: every row
+            assert np.array_equal(self.p[lo:hi], rows), "interior rows depend on the halo"
         elif phase == 3:
             self.vel = O.subtract_gradient(self.vel, self.p, self.obs)
 
@@ -101,15 +118,16 @@ def _reference():
     return vel, obs, div, p, out
 
 
-def _worker(rank, world, port, errors):
+def _worker(rank, world, port, overlap, errors):
     try:
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         dist.init_process_group("gloo", rank=rank, world_size=world)
         vel, obs, div, p, out = _reference()
         row0, rows = partition_rows(H, world)[rank]
-        eng = NumpySlabEngine(vel, obs, row0, rows, HALO, H)
+        eng = NumpySlabEngine(vel, obs, row0, rows, HALO, H, overlap)
         slab = SlabSimulator(W, H, engine=eng, halo=HALO, depth=DEPTH)
         slab.iterations = ITER
+        assert slab.overlap == overlap
         assert (slab.row0, slab.rows) == (row0, rows)
         slab.update(1.0 / 60.0)
         assert np.array_equal(eng.own(eng.div), div[row0:row0 + rows]), "divergence"
@@ -133,12 +151,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_slab_driver_matches_single_process_oracle_over_gloo(world):
+@pytest.mark.parametrize("world,overlap", [(2, False), (3, False), (2, True), (3, True)])
+def test_slab_driver_matches_single_process_oracle_over_gloo(world, overlap):
     ctx = mp.get_context("spawn")
     errors = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, errors)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, overlap, errors)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
