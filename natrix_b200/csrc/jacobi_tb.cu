@@ -613,7 +613,7 @@ struct JacobiTB {
         if (cudaMalloc((void**)&p.d_tiles, p.tiles.size() * sizeof(int4)) != cudaSuccess) { err = "cudaMalloc(tile plan)"; return nullptr; }
         if (cudaMemcpyAsync(p.d_tiles, p.tiles.data(), p.tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, st) != cudaSuccess ||
             cudaStreamSynchronize(st) != cudaSuccess) { err = "tile plan upload failed"; cudaFree(p.d_tiles); return nullptr; }
-        if (plans.size() >= 16) {                 // evict the oldest; the stream is idle after the sync above
+        if (plans.size() >= 128) {                // evict the oldest; the stream is idle after the sync above
             cudaFree(plans.front().d_tiles);
             plans.erase(plans.begin());
         }

@@ -1,5 +1,6 @@
 """Multi-GPU parity (pytest -m gpu, skipped with fewer than 2 devices): torchrun over NCCL, the
 slab run must be bit-identical to the single-GPU run (scripts/slab_check.py)."""
+import os
 import subprocess
 import sys
 
@@ -16,12 +17,14 @@ def _ngpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_slabs_bit_identical_to_single_gpu(world):
+@pytest.mark.parametrize("world,overlap", [(2, 1), (2, 0), (4, 1)])
+def test_slabs_bit_identical_to_single_gpu(world, overlap):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world), str(ROOT / "scripts" / "slab_check.py"),
            "1024", "1024", "3", "37"]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    # overlap 1: pressure exchanges overlapped with interior Jacobi launches (natrix_step_phase 4 / 5); 0: serial
+    env = dict(os.environ, NATRIX_SLAB_OVERLAP=str(overlap))
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0 and "SLAB_CHECK PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
