@@ -142,6 +142,16 @@ int natrix_field_stats(natrix_sim* sim, int field, double* out4);
  * velocity grid; it reads the simulator's CURRENT velocity and obstacle buffers (the
  * reference relies on the slot-1 / slot-7 bindings the simulator left behind). */
 int natrix_dye_create(natrix_sim* sim, int width, int height, natrix_dye** out);
+/* Multi-GPU: the rows [row0, row0+rows) of a width x global_height dye grid, with `halo`
+ * extra rows either side, attached to a simulator slab.  Before natrix_dye_step the host exchanges
+ * natrix_dye_halo_rows_needed(dye, 0, ..) rows of the simulator's VELOCITY (natrix_halo_region; take the
+ * maximum over ranks) and (dye, 1, ..) rows of the dye (natrix_dye_halo_region) with both neighbours.
+ * field_ptr / copy_out / copy_in / stats / export_rgba8 then cover the slab's own rows only. */
+int natrix_dye_create_slab(natrix_sim* sim, int width, int global_height, int row0, int rows, int halo,
+                           natrix_dye** out);
+int natrix_dye_halo_rows_needed(natrix_dye* dye, int which, float dt, float speed);
+int natrix_dye_halo_region(natrix_dye* dye, int side, int rows, void** send_ptr, void** recv_ptr,
+                           size_t* bytes);
 int natrix_dye_destroy(natrix_dye* dye);
 int natrix_dye_add(natrix_dye* dye, float px, float py, float radius, float strength);
 int natrix_dye_step(natrix_dye* dye, float dt, float speed, float dissipation);

@@ -41,6 +41,9 @@ SIGNATURES = {
     "natrix_copy_in": (_i, [_vp, _i, _vp, _sz]),
     "natrix_field_stats": (_i, [_vp, _i, _pd]),
     "natrix_dye_create": (_i, [_vp, _i, _i, _pvp]),
+    "natrix_dye_create_slab": (_i, [_vp, _i, _i, _i, _i, _i, _pvp]),
+    "natrix_dye_halo_rows_needed": (_i, [_vp, _i, _f, _f]),
+    "natrix_dye_halo_region": (_i, [_vp, _i, _i, _pvp, _pvp, _psz]),
     "natrix_dye_destroy": (_i, [_vp]),
     "natrix_dye_add": (_i, [_vp, _f, _f, _f, _f]),
     "natrix_dye_step": (_i, [_vp, _f, _f, _f]),

@@ -94,12 +94,18 @@ struct natrix_sim {
 
 struct natrix_dye {
     natrix_sim* sim = nullptr;
-    int w = 0, h = 0;
-    float* d[2] = {nullptr, nullptr};
-    float* tables = nullptr;                    // normalised x (w floats) then y (h floats) coordinates
+    Geom g{};                                   // dye rows held: w, global height, row0, rows, halo
+    float* base[2] = {nullptr, nullptr};        // allocations (halo rows included)
+    float* d[2] = {nullptr, nullptr};           // row-0 views
+    float* tables = nullptr;                    // normalised x (w floats) then y (one per own row) coordinates
     uint32_t* rgba = nullptr;                   // staging for host RGBA8 export
     int rd = 0;
     std::vector<SplatD> pending;
+
+    size_t own_cells() const { return (size_t)g.w * g.hl; }
+    // rows of the global dye grid this handle holds, as local indices (halo clipped at the grid's ends)
+    int held_lo() const { return g.y0 - g.halo < 0 ? -g.y0 : -g.halo; }
+    int held_hi() const { return g.y0 + g.hl + g.halo > g.hg ? g.hg - g.y0 : g.hl + g.halo; }
 };
 
 namespace {
@@ -203,16 +209,17 @@ int flush_circles(natrix_sim* s) {
 int flush_dye(natrix_dye* d) {
     natrix_sim* s = d->sim;
     size_t i = 0;
+    const int lo = d->held_lo(), hi = d->held_hi();      // halo rows too: both neighbours apply the same splats
     while (i < d->pending.size()) {
         if (s->pipeline == 0) {
             SplatDBatch b;
             b.n = 1;
             b.s[0] = d->pending[i++];
-            s->launches += launch_dye_add(d->d[d->rd], d->d[1 - d->rd], d->w, d->h, b, s->st);
+            s->launches += launch_dye_add(d->d[d->rd], d->d[1 - d->rd], d->g, lo, hi, b, s->st);
             d->rd = 1 - d->rd;
         } else {
             const int n = (int)std::min<size_t>(MAX_SPLATS, d->pending.size() - i);
-            s->launches += launch_splat_dye_boxes(d->d[d->rd], d->w, d->h, &d->pending[i], n, s->st);
+            s->launches += launch_splat_dye_boxes(d->d[d->rd], d->g, lo, hi, &d->pending[i], n, s->st);
             i += n;
         }
     }
@@ -830,31 +837,40 @@ int natrix_field_stats(natrix_sim* s, int field, double* out4) {
 }
 
 // ---- dye ---------------------------------------------------------------------------------------
-int natrix_dye_create(natrix_sim* s, int width, int height, natrix_dye** out) {
+int natrix_dye_create_slab(natrix_sim* s, int width, int global_height, int row0, int rows, int halo,
+                           natrix_dye** out) {
     NEED(s && out, "null argument");
     *out = nullptr;
-    NEED(width > 0 && height > 0, "width and height must be positive");
-    NEED(s->g.hl == s->g.hg, "dye fields need the full velocity grid on this device");
+    NEED(width > 0 && global_height > 0, "width and height must be positive");
+    NEED(row0 >= 0 && rows > 0 && row0 + rows <= global_height && halo >= 0, "bad dye slab geometry");
+    const bool full = rows == global_height;
+    NEED(full == (s->g.hl == s->g.hg), "a dye slab needs a simulator slab (and a full dye grid a full simulator)");
     if (int rc = select_device(s)) return rc;
     natrix_dye* d = new natrix_dye();
-    d->sim = s; d->w = width; d->h = height;
-    const size_t bytes = (size_t)width * height * sizeof(float);
-    for (int i = 0; i < 2; ++i) {
-        cudaError_t e = cudaMalloc((void**)&d->d[i], bytes);
-        if (e == cudaSuccess) e = cudaMemsetAsync(d->d[i], 0, bytes, s->st);
-        if (e != cudaSuccess) {
-            cudaFree(d->d[0]); cudaFree(d->d[1]); delete d;
-            return fail(NATRIX_ERR_CUDA, std::string("natrix_dye_create: ") + cudaGetErrorString(e));
-        }
+    d->sim = s;
+    d->g = Geom{width, global_height, row0, rows, halo};
+    const size_t cells = (size_t)width * ((size_t)rows + 2 * (size_t)halo);
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaMalloc((void**)&d->base[i], cells * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemsetAsync(d->base[i], 0, cells * sizeof(float), s->st);
+        d->d[i] = d->base[i] + (size_t)halo * width;
     }
-    if (cudaMalloc((void**)&d->tables, (size_t)(width + height) * sizeof(float)) != cudaSuccess) {
-        cudaFree(d->d[0]); cudaFree(d->d[1]); delete d;
-        return fail(NATRIX_ERR_CUDA, "natrix_dye_create: out of memory");
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d->tables, (size_t)(width + rows) * sizeof(float));
+    if (e != cudaSuccess) {
+        cudaFree(d->base[0]); cudaFree(d->base[1]); cudaFree(d->tables); delete d;
+        return fail(NATRIX_ERR_CUDA, std::string("natrix_dye_create: ") + cudaGetErrorString(e));
     }
-    s->launches += launch_dye_tables(d->tables, d->tables + width, width, height, s->g.w, s->g.hg, s->st);
+    s->launches += launch_dye_tables(d->tables, d->tables + width, d->g, s->g.w, s->g.hg, s->st);
     s->dyes.push_back(d);
     *out = d;
     return 0;
+}
+
+int natrix_dye_create(natrix_sim* s, int width, int height, natrix_dye** out) {
+    NEED(s, "null argument");
+    NEED(s->g.hl == s->g.hg, "dye fields on a simulator slab are created with natrix_dye_create_slab");
+    return natrix_dye_create_slab(s, width, height, 0, height, 0, out);
 }
 
 int natrix_dye_destroy(natrix_dye* d) {
@@ -865,7 +881,7 @@ int natrix_dye_destroy(natrix_dye* d) {
         auto& v = d->sim->dyes;
         for (size_t i = 0; i < v.size(); ++i) if (v[i] == d) { v.erase(v.begin() + i); break; }
     }
-    cudaFree(d->d[0]); cudaFree(d->d[1]); cudaFree(d->tables); cudaFree(d->rgba);
+    cudaFree(d->base[0]); cudaFree(d->base[1]); cudaFree(d->tables); cudaFree(d->rgba);
     delete d;
     return 0;
 }
@@ -874,7 +890,7 @@ int natrix_dye_destroy(natrix_dye* d) {
 
 int natrix_dye_add(natrix_dye* d, float px, float py, float radius, float strength) {
     DYE_LIVE(d);
-    SplatD sp{px * (float)d->w, py * (float)d->h, radius, strength};
+    SplatD sp{px * (float)d->g.w, py * (float)d->g.hg, radius, strength};
     d->pending.push_back(sp);
     if (d->sim->pipeline == 0) {
         if (int rc = select_device(d->sim)) return rc;
@@ -890,14 +906,58 @@ int natrix_dye_step(natrix_dye* d, float dt, float speed, float dissipation) {
     if (int rc = flush_splats(s)) return rc;     // the advect reads the CURRENT velocity
     if (int rc = flush_circles(s)) return rc;    // ... and the CURRENT obstacle map
     if (int rc = flush_dye(d)) return rc;
-    if (s->pipeline != 0 && d->w % 4 == 0)
-        s->launches += launch_dye_advect4(d->d[d->rd], d->d[1 - d->rd], d->w, d->h, s->vel[s->vr], s->obs, s->g.w,
-                                          s->g.hg, d->tables, d->tables + d->w, dt, speed, dissipation, s->st);
+    if (s->pipeline != 0 && d->g.w % 4 == 0)
+        s->launches += launch_dye_advect4(d->d[d->rd], d->d[1 - d->rd], d->g, s->vel[s->vr], s->obs, s->g, d->tables,
+                                          d->tables + d->g.w, dt, speed, dissipation, s->d_err, s->st);
     else
-        s->launches += launch_dye_advect(d->d[d->rd], d->d[1 - d->rd], d->w, d->h, s->vel[s->vr], s->obs, s->g.w,
-                                         s->g.hg, dt, speed, dissipation, s->st);
+        s->launches += launch_dye_advect(d->d[d->rd], d->d[1 - d->rd], d->g, s->vel[s->vr], s->obs, s->g, dt, speed,
+                                         dissipation, s->d_err, s->st);
     d->rd = 1 - d->rd;
     CU(cudaGetLastError());
+    if (s->g.hl != s->g.hg) return check_range_flag(s, false);
+    return 0;
+}
+
+// Halo rows a dye slab needs before natrix_dye_step: which = 0 rows of the simulator's VELOCITY (post
+// projection) around the rows the dye samples, 1 rows of the dye itself (back-trace reach + bilinear).
+// The velocity figure depends on how the two grids are cut: the host takes the maximum over ranks.
+int natrix_dye_halo_rows_needed(natrix_dye* d, int which, float dt, float speed) {
+    if (!d || !d->sim) return fail(NATRIX_ERR_ARG, "dye handle is null or its simulator was destroyed");
+    const Geom& g = d->g;
+    const Geom& vg = d->sim->g;
+    if (which == 0) {
+        // the shader's float32 expression for the first and last own dye row (monotone in y)
+        const float lo = ((float)g.y0 / (float)g.hg) * (float)vg.hg;
+        const float hi = ((float)(g.y0 + g.hl - 1) / (float)g.hg) * (float)vg.hg;
+        const int first = std::max(0, (int)std::floor(lo)), last = std::min(vg.hg - 1, (int)std::ceil(hi));
+        return std::max(0, std::max(vg.y0 - first, last - (vg.y0 + vg.hl - 1)));
+    }
+    if (which == 1) {
+        const double ry = (double)g.hg / (double)vg.hg;
+        return (int)std::ceil(1.25 * (double)dt * (double)speed * ry) + 2;
+    }
+    return fail(NATRIX_ERR_ARG, "which must be 0 (velocity) or 1 (dye)");
+}
+
+// As natrix_halo_region, for the dye rows.  Pending add_particles calls are applied first so that both
+// neighbours exchange the same state.
+int natrix_dye_halo_region(natrix_dye* d, int side, int rows, void** send_ptr, void** recv_ptr, size_t* bytes) {
+    DYE_LIVE(d);
+    NEED(send_ptr && recv_ptr && bytes, "null argument");
+    NEED(side == 0 || side == 1, "side must be 0 or 1");
+    NEED(rows >= 0 && rows <= d->g.halo && rows <= d->g.hl, "rows exceed the dye slab's halo");
+    if (int rc = select_device(d->sim)) return rc;
+    if (int rc = flush_dye(d)) return rc;
+    const size_t row_bytes = (size_t)d->g.w * sizeof(float);
+    char* base = (char*)d->d[d->rd];
+    if (side == 0) {
+        *send_ptr = base;
+        *recv_ptr = base - (ptrdiff_t)rows * (ptrdiff_t)row_bytes;
+    } else {
+        *send_ptr = base + (size_t)(d->g.hl - rows) * row_bytes;
+        *recv_ptr = base + (size_t)d->g.hl * row_bytes;
+    }
+    *bytes = (size_t)rows * row_bytes;
     return 0;
 }
 
@@ -907,13 +967,13 @@ int natrix_dye_field_ptr(natrix_dye* d, void** dev_ptr, size_t* bytes) {
     if (int rc = select_device(d->sim)) return rc;
     if (int rc = flush_dye(d)) return rc;
     *dev_ptr = d->d[d->rd];
-    if (bytes) *bytes = (size_t)d->w * d->h * sizeof(float);
+    if (bytes) *bytes = d->own_cells() * sizeof(float);
     return 0;
 }
 
 int natrix_dye_copy_out(natrix_dye* d, void* host, size_t bytes) {
     DYE_LIVE(d);
-    NEED(host && bytes == (size_t)d->w * d->h * sizeof(float), "dye copy_out size mismatch");
+    NEED(host && bytes == d->own_cells() * sizeof(float), "dye copy_out size mismatch");
     if (int rc = select_device(d->sim)) return rc;
     if (int rc = flush_dye(d)) return rc;
     CU(cudaMemcpyAsync(host, d->d[d->rd], bytes, cudaMemcpyDeviceToHost, d->sim->st));
@@ -923,7 +983,7 @@ int natrix_dye_copy_out(natrix_dye* d, void* host, size_t bytes) {
 
 int natrix_dye_copy_in(natrix_dye* d, const void* host, size_t bytes) {
     DYE_LIVE(d);
-    NEED(host && bytes == (size_t)d->w * d->h * sizeof(float), "dye copy_in size mismatch");
+    NEED(host && bytes == d->own_cells() * sizeof(float), "dye copy_in size mismatch");
     if (int rc = select_device(d->sim)) return rc;
     if (int rc = flush_dye(d)) return rc;
     CU(cudaMemcpyAsync(d->d[d->rd], host, bytes, cudaMemcpyHostToDevice, d->sim->st));
@@ -937,7 +997,7 @@ int natrix_dye_stats(natrix_dye* d, double* out4) {
     natrix_sim* s = d->sim;
     if (int rc = select_device(s)) return rc;
     if (int rc = flush_dye(d)) return rc;
-    s->launches += launch_stats(d->d[d->rd], (size_t)d->w * d->h, s->d_scratch, s->d_out4, s->st);
+    s->launches += launch_stats(d->d[d->rd], d->own_cells(), s->d_scratch, s->d_out4, s->st);
     CU(cudaMemcpyAsync(s->h_out4, s->d_out4, 4 * sizeof(double), cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
     memcpy(out4, s->h_out4, 4 * sizeof(double));
@@ -946,8 +1006,8 @@ int natrix_dye_stats(natrix_dye* d, double* out4) {
 
 int natrix_dye_export_rgba8(natrix_dye* d, void* out, size_t bytes, int is_device) {
     DYE_LIVE(d);
-    const size_t n = (size_t)d->w * d->h;
-    NEED(out && bytes == n * 4, "rgba8 export expects width*height*4 bytes");
+    const size_t n = d->own_cells();
+    NEED(out && bytes == n * 4, "rgba8 export expects width*rows*4 bytes");
     natrix_sim* s = d->sim;
     if (int rc = select_device(s)) return rc;
     if (int rc = flush_dye(d)) return rc;

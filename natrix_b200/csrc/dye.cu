@@ -8,17 +8,30 @@ namespace {
 
 constexpr int BX = 64, BY = 4, BT = BX * BY;   // 2-D blocks: back-traced gathers of nearby rows hit L1
 
+// Geometry: dg describes the dye rows this handle holds (w = dye width, hg = global dye height, rows
+// [y0, y0 + hl) plus `halo` rows either side), vg the simulator's velocity rows.  Arrays are indexed by
+// local row; the arithmetic only ever sees GLOBAL cell coordinates, so a slab reproduces the full grid.
+// A gather that leaves the held rows raises *err (slabs only: the full grid cannot trip it).
+__device__ __forceinline__ int held_row(const Geom& g, int gy, int* __restrict__ err) {
+    const int lo = g.y0 - g.halo, hi = g.y0 + g.hl + g.halo - 1;
+    if (gy < lo || gy > hi) {
+        *err = 1;
+        gy = clampi(gy, lo, hi);
+    }
+    return gy - g.y0;
+}
+
 // K splats applied in sequence per cell: identical arithmetic to K AddParticle dispatches
 // (each dispatch is a pure per-cell map, the ping-pong flip carries no cross-cell dependency).
 __global__ void __launch_bounds__(BT)
-k_dye_add(const float* __restrict__ din, float* __restrict__ dout, int pw, int ph,
+k_dye_add(const float* __restrict__ din, float* __restrict__ dout, const Geom dg, int r0, int r1,
           const __grid_constant__ SplatDBatch b) {
     const int x = blockIdx.x * BX + threadIdx.x;
-    const int y = blockIdx.y * BY + threadIdx.y;
-    if (x >= pw || y >= ph) return;
-    const size_t pos = (size_t)y * pw + x;
+    const int y = r0 + blockIdx.y * BY + threadIdx.y;
+    if (x >= dg.w || y >= r1) return;
+    const ptrdiff_t pos = lin(dg, x, y);
     float v = din[pos];
-    const float fxp = (float)x, fyp = (float)y;
+    const float fxp = (float)x, fyp = (float)(y + dg.y0);
     for (int i = 0; i < b.n; ++i) {
         const SplatD s = b.s[i];
         const float ex = s.sx - fxp, ey = s.sy - fyp;
@@ -29,31 +42,34 @@ k_dye_add(const float* __restrict__ din, float* __restrict__ dout, int pw, int p
 }
 
 __global__ void __launch_bounds__(BT)
-k_dye_advect(const float* __restrict__ din, float* __restrict__ dout, int pw, int ph,
-             const float2* __restrict__ vel, const uint8_t* __restrict__ obs, int vw, int vh,
-             float dt, float speed, float diss) {
+k_dye_advect(const float* __restrict__ din, float* __restrict__ dout, const Geom dg,
+             const float2* __restrict__ vel, const uint8_t* __restrict__ obs, const Geom vg,
+             float dt, float speed, float diss, int* __restrict__ err) {
     const int x = blockIdx.x * BX + threadIdx.x;
     const int y = blockIdx.y * BY + threadIdx.y;
-    if (x >= pw || y >= ph) return;
-    const size_t pos = (size_t)y * pw + x;
+    if (x >= dg.w || y >= dg.hl) return;
+    const int pw = dg.w, ph = dg.hg, vw = vg.w, vh = vg.hg;
+    const int gy = y + dg.y0;
+    const ptrdiff_t pos = lin(dg, x, y);
     // fNormalisedPos (:46) and the obstacle lookup at its truncation (:47-50)
     const float nx = ((float)x / (float)pw) * (float)vw;
-    const float ny = ((float)y / (float)ph) * (float)vh;
-    const size_t opos = (size_t)(unsigned)ny * vw + (unsigned)nx;
-    if (obs[opos] != OBS_FREE) { dout[pos] = 0.0f; return; }
+    const float ny = ((float)gy / (float)ph) * (float)vh;
+    if (obs[lin(vg, (int)(unsigned)nx, held_row(vg, (int)(unsigned)ny, err))] != OBS_FREE) { dout[pos] = 0.0f; return; }
     // GetVelocity (:21-35): bilinear sample of the velocity grid, scaled to dye cells
     const Corners c = corners(nx, ny, vw, vh);
-    const float2 lt = vel[(size_t)c.ty * vw + c.bx], rt = vel[(size_t)c.ty * vw + c.tx];
-    const float2 lb = vel[(size_t)c.by * vw + c.bx], rb = vel[(size_t)c.by * vw + c.tx];
+    const int vty = held_row(vg, c.ty, err), vby = held_row(vg, c.by, err);
+    const float2 lt = vel[lin(vg, c.bx, vty)], rt = vel[lin(vg, c.tx, vty)];
+    const float2 lb = vel[lin(vg, c.bx, vby)], rb = vel[lin(vg, c.tx, vby)];
     const float rx = (float)pw / (float)vw, ry = (float)ph / (float)vh;
     const float vx = mixf(mixf(lb.x, rb.x, c.dx), mixf(lt.x, rt.x, c.dx), c.dy) * rx;
     const float vy = mixf(mixf(lb.y, rb.y, c.dx), mixf(lt.y, rt.y, c.dx), c.dy) * ry;
     // back-trace in dye cells and gather the dye with the same clamp rule (:57-69)
     const float fx = (float)x - vx * dt * speed;
-    const float fy = (float)y - vy * dt * speed;
+    const float fy = (float)gy - vy * dt * speed;
     const Corners q = corners(fx, fy, pw, ph);
-    const float g1 = mixf(din[(size_t)q.ty * pw + q.bx], din[(size_t)q.ty * pw + q.tx], q.dx);
-    const float g2 = mixf(din[(size_t)q.by * pw + q.bx], din[(size_t)q.by * pw + q.tx], q.dx);
+    const int dty = held_row(dg, q.ty, err), dby = held_row(dg, q.by, err);
+    const float g1 = mixf(din[lin(dg, q.bx, dty)], din[lin(dg, q.tx, dty)], q.dx);
+    const float g2 = mixf(din[lin(dg, q.bx, dby)], din[lin(dg, q.tx, dby)], q.dx);
     dout[pos] = mixf(g2, g1, q.dy) * diss;
 }
 
@@ -62,26 +78,29 @@ k_dye_advect(const float* __restrict__ din, float* __restrict__ dout, int pw, in
 // thread, and the normalised coordinates come from tables filled by k_dye_tables with the exact
 // expression of the shader, so no per-cell IEEE division is left.
 constexpr int D4X = 32, D4Y = 8;
-__global__ void k_dye_tables(float* __restrict__ nx, float* __restrict__ ny, int pw, int ph, int vw, int vh) {
+__global__ void k_dye_tables(float* __restrict__ nx, float* __restrict__ ny, const Geom dg, int vw, int vh) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < pw) nx[i] = ((float)i / (float)pw) * (float)vw;        // fNormalisedPos.x (:46)
-    if (i < ph) ny[i] = ((float)i / (float)ph) * (float)vh;
+    if (i < dg.w) nx[i] = ((float)i / (float)dg.w) * (float)vw;        // fNormalisedPos.x (:46)
+    if (i < dg.hl) ny[i] = ((float)(i + dg.y0) / (float)dg.hg) * (float)vh;
 }
 
 __global__ void __launch_bounds__(D4X * D4Y)
-k_dye_advect4(const float* __restrict__ din, float* __restrict__ dout, int pw, int ph, const float2* __restrict__ vel,
-              const uint8_t* __restrict__ obs, int vw, int vh, const float* __restrict__ nxt,
-              const float* __restrict__ nyt, float rx, float ry, float dt, float speed, float diss) {
+k_dye_advect4(const float* __restrict__ din, float* __restrict__ dout, const Geom dg, const float2* __restrict__ vel,
+              const uint8_t* __restrict__ obs, const Geom vg, const float* __restrict__ nxt,
+              const float* __restrict__ nyt, float rx, float ry, float dt, float speed, float diss,
+              int* __restrict__ err) {
     const int x0 = (blockIdx.x * D4X + threadIdx.x) * 4;
     const int y = blockIdx.y * D4Y + threadIdx.y;
-    if (x0 >= pw || y >= ph) return;
+    if (x0 >= dg.w || y >= dg.hl) return;
+    const int pw = dg.w, ph = dg.hg, vw = vg.w, vh = vg.hg;
+    const int gy = y + dg.y0;
     const float ny = nyt[y];
     const float my = (float)(vh - 1), mx = (float)(vw - 1);
     const int vty = (int)clampf(ceilf(ny), 0.0f, my), vby = (int)clampf(floorf(ny), 0.0f, my);
     const float vdy = ny - (float)vby;
-    const float2* vrow_t = vel + (size_t)vty * vw;
-    const float2* vrow_b = vel + (size_t)vby * vw;
-    const uint8_t* orow = obs + (size_t)(unsigned)ny * vw;
+    const float2* vrow_t = vel + lin(vg, 0, held_row(vg, vty, err));
+    const float2* vrow_b = vel + lin(vg, 0, held_row(vg, vby, err));
+    const uint8_t* orow = obs + lin(vg, 0, held_row(vg, (int)(unsigned)ny, err));
     const float4 nx4 = *reinterpret_cast<const float4*>(nxt + x0);       // pw % 4 == 0
     const float nxs[4] = {nx4.x, nx4.y, nx4.z, nx4.w};
     float out[4];
@@ -94,16 +113,16 @@ k_dye_advect4(const float* __restrict__ din, float* __restrict__ dout, int pw, i
         const float vx = mixf(mixf(lb.x, rb.x, vdx), mixf(lt.x, rt.x, vdx), vdy) * rx;
         const float vy = mixf(mixf(lb.y, rb.y, vdx), mixf(lt.y, rt.y, vdx), vdy) * ry;
         const float fx = (float)(x0 + j) - vx * dt * speed;
-        const float fy = (float)y - vy * dt * speed;
+        const float fy = (float)gy - vy * dt * speed;
         const Corners q = corners(fx, fy, pw, ph);
-        const float* drow_t = din + (size_t)q.ty * pw;
-        const float* drow_b = din + (size_t)q.by * pw;
+        const float* drow_t = din + lin(dg, 0, held_row(dg, q.ty, err));
+        const float* drow_b = din + lin(dg, 0, held_row(dg, q.by, err));
         const float g1 = mixf(drow_t[q.bx], drow_t[q.tx], q.dx);
         const float g2 = mixf(drow_b[q.bx], drow_b[q.tx], q.dx);
         const float r = mixf(g2, g1, q.dy) * diss;
         out[j] = orow[(unsigned)nx] != OBS_FREE ? 0.0f : r;
     }
-    stg_stream(reinterpret_cast<float4*>(dout + (size_t)y * pw + x0), make_float4(out[0], out[1], out[2], out[3]));
+    stg_stream(reinterpret_cast<float4*>(dout + lin(dg, x0, y)), make_float4(out[0], out[1], out[2], out[3]));
 }
 
 // ref: demo/shaders/demo.ComputeShader.comp:9-21 - the dye value replicated into the four channels of
@@ -123,28 +142,29 @@ int launch_dye_rgba8(const float* dye, uint32_t* out, size_t n, cudaStream_t st)
     return 1;
 }
 
-int launch_dye_add(const float* din, float* dout, int pw, int ph, const SplatDBatch& b, cudaStream_t st) {
-    dim3 grid((pw + BX - 1) / BX, (ph + BY - 1) / BY, 1);
-    k_dye_add<<<grid, dim3(BX, BY, 1), 0, st>>>(din, dout, pw, ph, b);
+int launch_dye_add(const float* din, float* dout, Geom dg, int r0, int r1, const SplatDBatch& b, cudaStream_t st) {
+    if (r1 <= r0) return 0;
+    dim3 grid((dg.w + BX - 1) / BX, (r1 - r0 + BY - 1) / BY, 1);
+    k_dye_add<<<grid, dim3(BX, BY, 1), 0, st>>>(din, dout, dg, r0, r1, b);
     return 1;
 }
-int launch_dye_advect(const float* din, float* dout, int pw, int ph, const float2* vel, const uint8_t* obs,
-                      int vw, int vh, float dt, float speed, float diss, cudaStream_t st) {
-    dim3 grid((pw + BX - 1) / BX, (ph + BY - 1) / BY, 1);
-    k_dye_advect<<<grid, dim3(BX, BY, 1), 0, st>>>(din, dout, pw, ph, vel, obs, vw, vh, dt, speed, diss);
+int launch_dye_advect(const float* din, float* dout, Geom dg, const float2* vel, const uint8_t* obs, Geom vg,
+                      float dt, float speed, float diss, int* err, cudaStream_t st) {
+    dim3 grid((dg.w + BX - 1) / BX, (dg.hl + BY - 1) / BY, 1);
+    k_dye_advect<<<grid, dim3(BX, BY, 1), 0, st>>>(din, dout, dg, vel, obs, vg, dt, speed, diss, err);
     return 1;
 }
-int launch_dye_tables(float* nx, float* ny, int pw, int ph, int vw, int vh, cudaStream_t st) {
-    const int n = pw > ph ? pw : ph;
-    k_dye_tables<<<(n + 255) / 256, 256, 0, st>>>(nx, ny, pw, ph, vw, vh);
+int launch_dye_tables(float* nx, float* ny, Geom dg, int vw, int vh, cudaStream_t st) {
+    const int n = dg.w > dg.hl ? dg.w : dg.hl;
+    k_dye_tables<<<(n + 255) / 256, 256, 0, st>>>(nx, ny, dg, vw, vh);
     return 1;
 }
-int launch_dye_advect4(const float* din, float* dout, int pw, int ph, const float2* vel, const uint8_t* obs, int vw,
-                       int vh, const float* nx, const float* ny, float dt, float speed, float diss, cudaStream_t st) {
+int launch_dye_advect4(const float* din, float* dout, Geom dg, const float2* vel, const uint8_t* obs, Geom vg,
+                       const float* nx, const float* ny, float dt, float speed, float diss, int* err, cudaStream_t st) {
     // _ParticleSize / _VelocitySize (:34): IEEE single division, same on host and device
-    const float rx = (float)pw / (float)vw, ry = (float)ph / (float)vh;
-    dim3 grid((pw / 4 + D4X - 1) / D4X, (ph + D4Y - 1) / D4Y, 1);
-    k_dye_advect4<<<grid, dim3(D4X, D4Y, 1), 0, st>>>(din, dout, pw, ph, vel, obs, vw, vh, nx, ny, rx, ry, dt, speed, diss);
+    const float rx = (float)dg.w / (float)vg.w, ry = (float)dg.hg / (float)vg.hg;
+    dim3 grid((dg.w / 4 + D4X - 1) / D4X, (dg.hl + D4Y - 1) / D4Y, 1);
+    k_dye_advect4<<<grid, dim3(D4X, D4Y, 1), 0, st>>>(din, dout, dg, vel, obs, vg, nx, ny, rx, ry, dt, speed, diss, err);
     return 1;
 }
 

@@ -300,17 +300,17 @@ k_clamp_outside_boxes(float2* __restrict__ vel, const Geom g, int r0, int r1, co
 
 // ref: demo/shaders/shader.AddParticle.comp:25-34, b.n dispatches in order, in place, boxes only
 __global__ void __launch_bounds__(SBX * SBY)
-k_splat_dye_boxes(float* __restrict__ dye, int pw, const __grid_constant__ SplatDBoxes b) {
+k_splat_dye_boxes(float* __restrict__ dye, const Geom dg, const __grid_constant__ SplatDBoxes b) {
     const int i = blockIdx.z;
-    const Box bx = b.b[i];
+    const Box bx = b.b[i];                       // boxes are in global dye cells, clipped to the rows held
     const int x = bx.x0 + blockIdx.x * SBX + threadIdx.x;
-    const int y = bx.y0 + blockIdx.y * SBY + threadIdx.y;
-    if (x >= bx.x1 || y >= bx.y1) return;
+    const int gy = bx.y0 + blockIdx.y * SBY + threadIdx.y;
+    if (x >= bx.x1 || gy >= bx.y1) return;
     for (int k = 0; k < i; ++k)
-        if (in_box(b.b[k], x, y)) return;
-    const size_t pos = (size_t)y * pw + x;
+        if (in_box(b.b[k], x, gy)) return;
+    const ptrdiff_t pos = lin(dg, x, gy - dg.y0);
     float v = dye[pos];
-    const float fxp = (float)x, fyp = (float)y;
+    const float fxp = (float)x, fyp = (float)gy;
     for (int k = 0; k < b.n; ++k) {
         const SplatD s = b.s[k];
         const float ex = s.sx - fxp, ey = s.sy - fyp;
@@ -545,17 +545,17 @@ int launch_add_circles(uint8_t* obs, Geom g, int r0, int r1, const float* sxyr, 
     return launched;
 }
 
-int launch_splat_dye_boxes(float* dye, int pw, int ph, const SplatD* splats, int n, cudaStream_t st) {
-    if (n <= 0) return 0;
+int launch_splat_dye_boxes(float* dye, Geom dg, int r0, int r1, const SplatD* splats, int n, cudaStream_t st) {
+    if (n <= 0 || r1 <= r0) return 0;
     SplatDBoxes b;
     b.n = n;
     for (int i = 0; i < n; ++i) {
         b.s[i] = splats[i];
-        b.b[i] = splat_box(splats[i].sx, splats[i].sy, splats[i].r, 0, pw, 0, ph);
+        b.b[i] = splat_box(splats[i].sx, splats[i].sy, splats[i].r, 0, dg.w, dg.y0 + r0, dg.y0 + r1);
     }
     const dim3 grid = boxes_grid(b);
     if (grid.x == 0 || grid.y == 0) return 0;
-    k_splat_dye_boxes<<<grid, dim3(SBX, SBY, 1), 0, st>>>(dye, pw, b);
+    k_splat_dye_boxes<<<grid, dim3(SBX, SBY, 1), 0, st>>>(dye, dg, b);
     return 1;
 }
 

@@ -42,18 +42,17 @@ int launch_obs_pack(const float2* in, uint8_t* obs, size_t n, cudaStream_t st);
 int launch_stats(const float* data, size_t n, double* scratch, double* out4_dev, cudaStream_t st);
 
 // ---- dye (dye.cu) ----------------------------------------------------------------------------
-int launch_dye_add(const float* din, float* dout, int pw, int ph, const SplatDBatch& b,
-                   cudaStream_t st);
-int launch_dye_advect(const float* din, float* dout, int pw, int ph, const float2* vel,
-                      const uint8_t* obs, int vw, int vh, float dt, float speed, float diss,
-                      cudaStream_t st);
+// dg: the dye rows held (Geom of the dye grid), vg: the simulator's velocity rows; arrays are row-0 views.
+// err: device int raised when a gather leaves the held rows (slabs only).
+int launch_dye_add(const float* din, float* dout, Geom dg, int r0, int r1, const SplatDBatch& b, cudaStream_t st);
+int launch_dye_advect(const float* din, float* dout, Geom dg, const float2* vel, const uint8_t* obs, Geom vg,
+                      float dt, float speed, float diss, int* err, cudaStream_t st);
 
 int launch_dye_rgba8(const float* dye, uint32_t* out, size_t n, cudaStream_t st);
 // 4 cells per thread with precomputed normalised-coordinate tables (width % 4 == 0)
-int launch_dye_tables(float* nx, float* ny, int pw, int ph, int vw, int vh, cudaStream_t st);
-int launch_dye_advect4(const float* din, float* dout, int pw, int ph, const float2* vel, const uint8_t* obs,
-                       int vw, int vh, const float* nx, const float* ny, float dt, float speed, float diss,
-                       cudaStream_t st);
+int launch_dye_tables(float* nx, float* ny, Geom dg, int vw, int vh, cudaStream_t st);
+int launch_dye_advect4(const float* din, float* dout, Geom dg, const float2* vel, const uint8_t* obs, Geom vg,
+                       const float* nx, const float* ny, float dt, float speed, float diss, int* err, cudaStream_t st);
 
 // ---- fused pipeline (fused.cu / jacobi_tb.cu) ----------------------------------------------------
 int launch_poisson_mask(const float* pin, const float* div, const uint8_t* nbmask, float* pout,
@@ -71,7 +70,7 @@ int launch_zero_borders(float2* vel, Geom g, int r0, int r1, cudaStream_t st);
 // in-place impulses restricted to the splats' bounding boxes (n <= MAX_SPLATS)
 int launch_splat_velocity_boxes(float2* vel, Geom g, int r0, int r1, const SplatV* splats, int n,
                                 const int* over1, int sm_count, cudaStream_t st);
-int launch_splat_dye_boxes(float* dye, int pw, int ph, const SplatD* splats, int n, cudaStream_t st);
+int launch_splat_dye_boxes(float* dye, Geom dg, int r0, int r1, const SplatD* splats, int n, cudaStream_t st);
 // n queued circles (sx, sy, radius triples, in cells) rasterised on their bounding boxes, rows [r0, r1)
 int launch_add_circles(uint8_t* obs, Geom g, int r0, int r1, const float* sxyr, int n, cudaStream_t st);
 

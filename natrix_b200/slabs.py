@@ -145,15 +145,18 @@ class SlabSimulator:
             self.sim.add_triangle_obstacle(p1, p2, p3, static)
 
     # -- halo exchange with the two neighbouring ranks
-    def exchange(self, fields, rows: int, comm: bool = False):
+    def exchange(self, fields, rows: int, comm: bool = False, region=None, limit: Optional[int] = None):
         """Swap `rows` halo rows of one field (or of several, in one batched NCCL group) with both neighbours,
-        on the simulator's stream or (comm=True) on its second stream."""
+        on the simulator's stream or (comm=True) on its second stream.  `region(field, side, rows)` returns
+        the (send, recv) buffers; the default asks the simulator's engine."""
         if isinstance(fields, str):
             fields = (fields,)
         if rows <= 0 or self.world == 1:
             return
-        if rows > self.halo:
-            raise ValueError(f"{'+'.join(fields)}: step needs {rows} halo rows but the slab was created with {self.halo}")
+        limit = self.halo if limit is None else limit
+        if rows > limit:
+            raise ValueError(f"{'+'.join(fields)}: step needs {rows} halo rows but the slab was created with {limit}")
+        region = region or self.engine.halo_region
         dist = self.dist
         ops, keep = [], []
         with (self.engine.stream_context(True) if comm else self.engine.stream_context()):
@@ -161,7 +164,7 @@ class SlabSimulator:
                 if peer < 0 or peer >= self.world:
                     continue
                 for field in fields:
-                    send, recv = self.engine.halo_region(field, side, rows)
+                    send, recv = region(field, side, rows)
                     ops += [dist.P2POp(dist.isend, send, peer, self.group), dist.P2POp(dist.irecv, recv, peer, self.group)]
                     keep += [send, recv]
             for req in dist.batch_isend_irecv(ops):
@@ -194,6 +197,106 @@ class SlabSimulator:
             e.phase(5 if overlap else 2, time_delta, t)       # edge rows (or all rows) after the exchange
         self.exchange("pressure", 1)
         e.phase(3, time_delta)
+
+
+def velocity_rows_for_dye(dye_height: int, grid_height: int, world: int) -> int:
+    """Rows of post-projection velocity a dye slab samples beyond its simulator slab, maximum over ranks
+    (every rank must exchange the same count).  Mirrors natrix_dye_halo_rows_needed(dye, 0, ..): the
+    shader's float32 ``(y / dye_height) * grid_height`` at the first and last dye row of each slab
+    (ref: demo/shaders/shader.AdvectParticle.comp:46)."""
+    f32 = np.float32
+    need = 0
+    for (p0, pn), (v0, vn) in zip(partition_rows(dye_height, world), partition_rows(grid_height, world)):
+        lo = (f32(p0) / f32(dye_height)) * f32(grid_height)
+        hi = (f32(p0 + pn - 1) / f32(dye_height)) * f32(grid_height)
+        first, last = max(0, int(math.floor(lo))), min(grid_height - 1, int(math.ceil(hi)))
+        need = max(need, v0 - first, last - (v0 + vn - 1))
+    return need
+
+
+class CudaDyeSlabEngine:
+    """One dye slab handle of libnatrix_b200.so attached to a CudaSlabEngine's simulator slab."""
+
+    def __init__(self, width, height, row0, rows, halo, sim_engine: CudaSlabEngine):
+        from natrix_b200.smooth_particles_area import SmoothParticlesArea
+
+        self.e = sim_engine
+        self.area = SmoothParticlesArea(width, height, sim_engine.sim, None, slab=(row0, rows, halo))
+
+    def add(self, position, radius, strength):
+        self.area.add_particles(position, radius, strength)
+
+    def rows_needed(self, which: int, dt: float, speed: float) -> int:
+        L = self.e.L
+        return L.check(self.area._lib.natrix_dye_halo_rows_needed(self.area._handle(), which, dt, speed))
+
+    def halo_region(self, field, side: int, rows: int):
+        send, recv, nbytes = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        self.e.L.check(self.area._lib.natrix_dye_halo_region(self.area._handle(), side, rows, C.byref(send),
+                                                             C.byref(recv), C.byref(nbytes)))
+        return self.e._view(send.value, nbytes.value), self.e._view(recv.value, nbytes.value)
+
+    def step(self, dt: float, speed: float, dissipation: float):
+        self.e.L.check(self.area._lib.natrix_dye_step(self.area._handle(), dt, speed, dissipation))
+
+
+class SlabSmoothParticlesArea:
+    """The reference's SmoothParticlesArea surface (demo/smooth_particles_area.py:15-211) for one rank's slab
+    of a global dye grid, cut into the same normalised-y slabs as the simulator.
+
+    Per update: the post-projection velocity rows the dye samples beyond the simulator slab and the dye rows
+    within back-trace reach are exchanged with the two neighbours, then the slab's own rows are advected.
+    add_particles is a function of global coordinates: every rank applies it to the rows it holds."""
+
+    def __init__(self, width: int, height: int, fluid_simulation: SlabSimulator, vertex_layout=None,
+                 halo: Optional[int] = None, engine=None):
+        self.slab = fluid_simulation
+        self.width, self.height = int(width), int(height)
+        self.row0, self.rows = partition_rows(self.height, self.slab.world)[self.slab.rank]
+        ratio = self.height / self.slab.height
+        self.halo = int(math.ceil(self.slab.halo * max(1.0, ratio))) if halo is None else int(halo)
+        if self.rows < self.halo:
+            raise ValueError(f"dye slab of {self.rows} rows is shorter than its halo ({self.halo})")
+        self.velocity_rows = velocity_rows_for_dye(self.height, self.slab.height, self.slab.world)
+        if engine is None:
+            engine = CudaDyeSlabEngine(self.width, self.height, self.row0, self.rows, self.halo, self.slab.engine)
+        self.engine = engine
+        self._speed, self._dissipation = 500.0, 1.0
+        self.simulate = True
+
+    @property
+    def speed(self):
+        return self._speed
+
+    @speed.setter
+    def speed(self, value):
+        if value > 0:
+            self._speed = value
+        else:
+            raise ValueError("'Speed' should be greater than zero")
+
+    @property
+    def dissipation(self):
+        return self._dissipation
+
+    @dissipation.setter
+    def dissipation(self, value):
+        if value > 0:
+            self._dissipation = value
+        else:
+            raise ValueError("'Dissipation' should be grater than zero")
+
+    def add_particles(self, position, radius, strength):
+        if self.simulate:
+            self.engine.add(position, radius, strength)
+
+    def update(self, time_delta: float):
+        if not self.simulate:
+            return
+        self.slab.exchange("velocity", self.velocity_rows)
+        rows = self.engine.rows_needed(1, time_delta, self._speed)
+        self.slab.exchange("dye", rows, region=self.engine.halo_region, limit=self.halo)
+        self.engine.step(time_delta, self._speed, self._dissipation)
 
 
 # ----------------------------------------------------------------------------------------- bench

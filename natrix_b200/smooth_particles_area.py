@@ -23,7 +23,9 @@ class SmoothParticlesArea:
 
     simulate = True
 
-    def __init__(self, width: int, height: int, fluid_simulation: FluidSimulator, vertex_layout=None):
+    def __init__(self, width: int, height: int, fluid_simulation: FluidSimulator, vertex_layout=None, slab=None):
+        """``slab=(row0, rows, halo)`` holds one row slab of the ``width x height`` dye grid on a simulator
+        slab (multi-GPU, natrix_b200.slabs.SlabSmoothParticlesArea); buffers then cover ``rows`` rows."""
         self.fluid_simulation = fluid_simulation
         self.vertex_layout = vertex_layout
         self._width = int(width)
@@ -32,8 +34,15 @@ class SmoothParticlesArea:
         self._dissipation = 1.0
         self._lib = L.lib()
         handle = C.c_void_p()
-        L.check(self._lib.natrix_dye_create(fluid_simulation._handle(), self._width, self._height,
-                                            C.byref(handle)))
+        if slab is None:
+            self._rows = self._height
+            L.check(self._lib.natrix_dye_create(fluid_simulation._handle(), self._width, self._height,
+                                                C.byref(handle)))
+        else:
+            row0, rows, halo = (int(v) for v in slab)
+            self._rows = rows
+            L.check(self._lib.natrix_dye_create_slab(fluid_simulation._handle(), self._width, self._height, row0, rows,
+                                                     halo, C.byref(handle)))
         self._h = handle
         fluid_simulation._dyes.append(self)
 
@@ -97,7 +106,7 @@ class SmoothParticlesArea:
     def get_particles_buffer(self) -> DeviceField:
         ptr, nbytes = C.c_void_p(), C.c_size_t()
         L.check(self._lib.natrix_dye_field_ptr(self._handle(), C.byref(ptr), C.byref(nbytes)))
-        return DeviceField(ptr.value, (self._height, self._width), np.float32, self,
+        return DeviceField(ptr.value, (self._rows, self._width), np.float32, self,
                            self.fluid_simulation.cuda_stream)
 
     @property
@@ -108,18 +117,18 @@ class SmoothParticlesArea:
         return self.download()
 
     def download(self) -> np.ndarray:
-        out = np.empty((self._height, self._width), np.float32)
+        out = np.empty((self._rows, self._width), np.float32)
         L.check(self._lib.natrix_dye_copy_out(self._handle(), out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
 
     def upload(self, array) -> None:
-        arr = np.ascontiguousarray(array, dtype=np.float32).reshape(self._height, self._width)
+        arr = np.ascontiguousarray(array, dtype=np.float32).reshape(self._rows, self._width)
         L.check(self._lib.natrix_dye_copy_in(self._handle(), arr.ctypes.data_as(C.c_void_p), arr.nbytes))
 
     def export_rgba8(self) -> np.ndarray:
         """The dye as the (H, W, 4) uint8 image the demo's compute shader writes for rendering
         (ref: demo/shaders/demo.ComputeShader.comp:9-21)."""
-        out = np.empty((self._height, self._width, 4), np.uint8)
+        out = np.empty((self._rows, self._width, 4), np.uint8)
         L.check(self._lib.natrix_dye_export_rgba8(self._handle(), out.ctypes.data_as(C.c_void_p), out.nbytes, 0))
         return out
 

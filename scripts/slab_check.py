@@ -4,7 +4,8 @@
         --master-port 29511 scripts/slab_check.py [width height steps iterations]
 
 Every rank computes the single-GPU reference of the whole grid on its own device, then compares
-its slab's rows of every field after each step."""
+its slab's rows of every field - and of a dye field cut into the same slabs (2x the grid's resolution
+under pipeline 1, 1.5x under pipeline 0) - after each step."""
 import os
 import sys
 from pathlib import Path
@@ -16,7 +17,8 @@ import torch.distributed as dist  # noqa: E402
 
 from natrix_b200 import _lib as L, workloads as W  # noqa: E402
 from natrix_b200.core.fluid_simulator import FluidSimulator  # noqa: E402
-from natrix_b200.slabs import SlabSimulator  # noqa: E402
+from natrix_b200.slabs import SlabSimulator, SlabSmoothParticlesArea  # noqa: E402
+from natrix_b200.smooth_particles_area import SmoothParticlesArea  # noqa: E402
 
 width, height, steps, iters = (int(a) for a in (sys.argv[1:5] + ["1024", "2048", "3", "37"][len(sys.argv) - 1:]))
 rank, world, local = (int(os.environ.get(k, "0")) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
@@ -38,6 +40,10 @@ for pipeline in (1, 0):
     slab.iterations = iters
     ref.upload("velocity", v0)
     slab.sim.upload("velocity", v0[slab.row0:slab.row0 + slab.rows])
+    pw, ph = (2 * width, 2 * height) if pipeline else (3 * width // 2, 3 * height // 2)
+    ref_dye, slab_dye = SmoothParticlesArea(pw, ph, ref), SlabSmoothParticlesArea(pw, ph, slab)
+    for d in (ref_dye, slab_dye):
+        d.dissipation = 0.98
     for k in range(steps):
         for s in (ref, slab):
             for (px, py, r) in circles:
@@ -46,6 +52,10 @@ for pipeline in (1, 0):
             s.update(W.DT)
             for pos, vel, r in splats:
                 s.add_velocity(pos, vel, r)
+        for d in (ref_dye, slab_dye):
+            d.add_particles((0.5, 0.5), 0.2 * ph, 0.6)            # straddles the slab boundaries
+            d.add_particles((0.2, 0.74), 0.05 * ph, 0.9)
+            d.update(W.DT)
         for name in ("velocity", "pressure", "divergence", "vorticity"):
             a = ref.download(name)[slab.row0:slab.row0 + slab.rows]
             b = slab.sim.download(name)
@@ -54,6 +64,16 @@ for pipeline in (1, 0):
             if not same or k == steps - 1:
                 print(f"[rank {rank}/{world}] pipeline {pipeline} step {k} {name}: bit-identical={same} "
                       f"max|diff|={float(np.abs(a - b).max()):.3e} max|ref|={float(np.abs(a).max()):.3e}", flush=True)
+        a = ref_dye.download()[slab_dye.row0:slab_dye.row0 + slab_dye.rows]
+        b = slab_dye.engine.area.download()
+        same = bool(np.array_equal(a, b)) and bool(np.array_equal(
+            ref_dye.export_rgba8()[slab_dye.row0:slab_dye.row0 + slab_dye.rows], slab_dye.engine.area.export_rgba8()))
+        ok &= same
+        if not same or k == steps - 1:
+            print(f"[rank {rank}/{world}] pipeline {pipeline} step {k} dye {pw}x{ph}: bit-identical={same} "
+                  f"max|diff|={float(np.abs(a - b).max()):.3e} max|ref|={float(np.abs(a).max()):.3e}", flush=True)
+    ref_dye.destroy()
+    slab_dye.engine.area.destroy()
     ref.destroy()
     slab.sim.destroy()
 flag = torch.tensor([0 if ok else 1], device=f"cuda:{local}")

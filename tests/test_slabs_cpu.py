@@ -171,3 +171,132 @@ def test_slab_driver_matches_single_process_oracle_over_gloo(world, overlap):
         elif p.exitcode != 0:
             msgs.append(f"exit code {p.exitcode}")
     assert not msgs, "\n".join(msgs)
+
+
+# ------------------------------------------------------------------------------------------------ dye slabs
+PW, PH, VW, VH, DHALO, DSTEPS = 40, 90, 24, 45, 15, 3
+DYE_DT, DYE_SPEED = 1.0 / 60.0, 300.0
+
+
+class NumpyDyeRig:
+    """Simulator + dye stand-ins for SlabSmoothParticlesArea.  Every array has the GLOBAL shape, but only the
+    rows a rank holds carry data - the rest is poison (NaN dye, 1e6 velocity: a NaN velocity has no back-trace
+    cell), so any read outside the exchanged halos ruins the result.  Stages are the oracle's own functions
+    evaluated on those arrays."""
+
+    def __init__(self, rank, world, vel):
+        self.v0, self.vn = partition_rows(VH, world)[rank]
+        self.p0, self.pn = partition_rows(PH, world)[rank]
+        self.vel = np.full((VH, VW, 2), 1e6, np.float32)
+        self.vel[self.v0:self.v0 + self.vn] = vel[self.v0:self.v0 + self.vn]
+        self.obs = np.zeros((VH, VW, 2), np.float32)
+        self.dye = np.full((PH, PW), np.nan, np.float32)
+        self.dye[max(0, self.p0 - DHALO):self.p0 + self.pn + DHALO] = 0.0
+        self.sim = self
+
+    # -- simulator engine surface used by SlabSimulator.exchange
+    def stream_context(self, comm=False):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def halo_region(self, field, side, rows):
+        a, r0, rn = (self.vel, self.v0, self.vn) if field == "velocity" else (self.dye, self.p0, self.pn)
+        if side == 0:
+            send, recv = a[r0:r0 + rows], a[r0 - rows:r0]
+        else:
+            send, recv = a[r0 + rn - rows:r0 + rn], a[r0 + rn:r0 + rn + rows]
+        return torch.from_numpy(send), torch.from_numpy(recv)
+
+    # -- dye engine surface
+    def add(self, position, radius, strength):
+        with np.errstate(invalid="ignore"):
+            self.dye = O.add_particles(self.dye, position, radius, strength)
+
+    def rows_needed(self, which, dt, speed):
+        assert which == 1
+        return int(np.ceil(1.25 * dt * speed * PH / VH)) + 2
+
+    def step(self, dt, speed, dissipation):
+        with np.errstate(invalid="ignore"):
+            out = O.advect_particles(self.dye, self.vel, self.obs, dt, speed, dissipation)
+        own = out[self.p0:self.p0 + self.pn]
+        assert not np.isnan(own).any(), "the dye step read rows that were never exchanged"
+        self.dye = np.full_like(out, np.nan)
+        self.dye[self.p0:self.p0 + self.pn] = own
+        lo, hi = max(0, self.p0 - DHALO), min(PH, self.p0 + self.pn + DHALO)
+        self.dye[lo:self.p0] = 0.0                      # stale halo rows: finite garbage, refreshed by the next exchange
+        self.dye[self.p0 + self.pn:hi] = 0.0
+        self.vel[:self.v0] = 1e6                        # the velocity halo is only valid for this step
+        self.vel[self.v0 + self.vn:] = 1e6
+
+
+def _dye_reference():
+    rng = np.random.default_rng(9)
+    vel = rng.uniform(-1.0, 1.0, (VH, VW, 2)).astype(np.float32)
+    obs = np.zeros((VH, VW, 2), np.float32)
+    dye = np.zeros((PH, PW), np.float32)
+    frames = []
+    for k in range(DSTEPS):
+        dye = O.add_particles(dye, (0.5, 0.2 + 0.3 * k), 9.0, 0.7)
+        dye = O.add_particles(dye, (0.3, 0.5), 14.0, 0.4)
+        dye = O.advect_particles(dye, vel, obs, DYE_DT, DYE_SPEED, 0.97)
+        frames.append(dye)
+    return vel, frames
+
+
+def _dye_worker(rank, world, port, errors):
+    try:
+        from natrix_b200.slabs import SlabSmoothParticlesArea
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        vel, frames = _dye_reference()
+        rig = NumpyDyeRig(rank, world, vel)
+        slab = SlabSimulator(VW, VH, engine=rig, halo=6, depth=2)
+        area = SlabSmoothParticlesArea(PW, PH, slab, halo=DHALO, engine=rig)
+        area.speed, area.dissipation = DYE_SPEED, 0.97
+        assert (area.row0, area.rows) == (rig.p0, rig.pn) and area.velocity_rows >= 1
+        for k in range(DSTEPS):
+            area.add_particles((0.5, 0.2 + 0.3 * k), 9.0, 0.7)
+            area.add_particles((0.3, 0.5), 14.0, 0.4)
+            area.update(DYE_DT)
+            assert np.array_equal(rig.dye[rig.p0:rig.p0 + rig.pn], frames[k][rig.p0:rig.p0 + rig.pn]), f"dye, step {k}"
+        with pytest.raises(ValueError):
+            slab.exchange("dye", DHALO + 1, region=rig.halo_region, limit=DHALO)
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001 - reported to the parent
+        import traceback
+        errors.put(f"rank {rank}: {e}\n{traceback.format_exc()}")
+
+
+def _run_world(target, world, extra=()):
+    ctx = mp.get_context("spawn")
+    errors = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=target, args=(r, world, port, *extra, errors)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+    msgs = []
+    while not errors.empty():
+        msgs.append(errors.get())
+    for p in procs:
+        if p.is_alive():
+            p.terminate()
+            msgs.append("a rank hung")
+        elif p.exitcode != 0:
+            msgs.append(f"exit code {p.exitcode}")
+    assert not msgs, "\n".join(msgs)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_dye_slab_driver_matches_single_process_oracle_over_gloo(world):
+    _run_world(_dye_worker, world)
+
+
+def test_velocity_rows_for_dye():
+    from natrix_b200.slabs import velocity_rows_for_dye
+    assert velocity_rows_for_dye(4096, 4096, 8) == 0          # same grid: a dye row samples exactly its own velocity row
+    assert velocity_rows_for_dye(720, 360, 2) == 1            # the demo's 2x dye grid: one row below (ceil of x.5)
+    assert 1 <= velocity_rows_for_dye(1000, 360, 3) <= 2
