@@ -164,6 +164,14 @@ int natrix_dye_stats(natrix_dye* dye, double* out4);
  * ref: demo/shaders/demo.ComputeShader.comp:9-21 (imageStore(InputTexture, coord, vec4(v, v, v, v))).
  * `out` may be a device or a host pointer (is_device says which); bytes = width * height * 4. */
 int natrix_dye_export_rgba8(natrix_dye* dye, void* out, size_t bytes, int is_device);
+/* the frame the demo draws, as a width x height RGBA8 image (top row first) with
+ * the framebuffer taken to have the dye grid's size: the rgba8 dye texture above coloured by
+ * plasma(fbm(texel)) with alpha = texel (ref: demo/shaders/demo.FieldFragmentShader.frag:21-33,73-99),
+ * alpha-blended over the clear colour 0x1a0427ff (ref: demo/simulation_demo.py:94, :249-254) and, when
+ * quiver_tile > 0 (the demo offers 8, 16, 32, 64), the white velocity arrows of
+ * demo/shaders/demo.QuiverFragmentShader.frag:14-70 blended on top (simulation_demo.py:256-281).
+ * Full-grid handles only.  `out` may be a device or a host pointer; bytes = width * height * 4. */
+int natrix_render_frame(natrix_dye* dye, void* out, size_t bytes, int is_device, float quiver_tile);
 
 /* ---- synchronisation / introspection ------------------------------------------------- */
 int natrix_sync(natrix_sim* sim);

@@ -52,6 +52,7 @@ SIGNATURES = {
     "natrix_dye_copy_in": (_i, [_vp, _vp, _sz]),
     "natrix_dye_stats": (_i, [_vp, _pd]),
     "natrix_dye_export_rgba8": (_i, [_vp, _vp, _sz, _i]),
+    "natrix_render_frame": (_i, [_vp, _vp, _sz, _i, _f]),
     "natrix_sync": (_i, [_vp]),
     "natrix_stream": (_i, [_vp, _pvp]),
     "natrix_comm_stream": (_i, [_vp, _pvp]),

@@ -99,6 +99,7 @@ struct natrix_dye {
     float* d[2] = {nullptr, nullptr};           // row-0 views
     float* tables = nullptr;                    // normalised x (w floats) then y (one per own row) coordinates
     uint32_t* rgba = nullptr;                   // staging for host RGBA8 export
+    float4* lut = nullptr;                      // 256-entry field colour map (render.cu), built on first use
     int rd = 0;
     std::vector<SplatD> pending;
 
@@ -881,7 +882,7 @@ int natrix_dye_destroy(natrix_dye* d) {
         auto& v = d->sim->dyes;
         for (size_t i = 0; i < v.size(); ++i) if (v[i] == d) { v.erase(v.begin() + i); break; }
     }
-    cudaFree(d->base[0]); cudaFree(d->base[1]); cudaFree(d->tables); cudaFree(d->rgba);
+    cudaFree(d->base[0]); cudaFree(d->base[1]); cudaFree(d->tables); cudaFree(d->rgba); cudaFree(d->lut);
     delete d;
     return 0;
 }
@@ -1020,6 +1021,35 @@ int natrix_dye_export_rgba8(natrix_dye* d, void* out, size_t bytes, int is_devic
     s->launches += launch_dye_rgba8(d->d[d->rd], d->rgba, n, s->st);
     CU(cudaMemcpyAsync(out, d->rgba, bytes, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+
+int natrix_render_frame(natrix_dye* d, void* out, size_t bytes, int is_device, float quiver_tile) {
+    DYE_LIVE(d);
+    natrix_sim* s = d->sim;
+    NEED(s->g.hl == s->g.hg, "frames are rendered from the full grid (gather the slabs first)");
+    const size_t n = d->own_cells();
+    NEED(out && bytes == n * 4, "a frame is width*height*4 bytes");
+    if (int rc = select_device(s)) return rc;
+    if (int rc = flush_dye(d)) return rc;
+    if (quiver_tile > 0.0f)
+        if (int rc = flush_splats(s)) return rc;             // the overlay shows the CURRENT velocity
+    if (!d->lut) {
+        CU(cudaMalloc((void**)&d->lut, 256 * sizeof(float4)));
+        s->launches += launch_field_lut(d->lut, s->st);
+    }
+    uint32_t* dst = (uint32_t*)out;
+    if (!is_device) {
+        if (!d->rgba) CU(cudaMalloc((void**)&d->rgba, n * 4));
+        dst = d->rgba;
+    }
+    s->launches += launch_render_frame(d->d[d->rd], d->lut, s->vel[s->vr], dst, d->g.w, d->g.hl, s->g.w, s->g.hg,
+                                       quiver_tile, s->st);
+    CU(cudaGetLastError());
+    if (!is_device) {
+        CU(cudaMemcpyAsync(out, d->rgba, bytes, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaStreamSynchronize(s->st));
+    }
     return 0;
 }
 

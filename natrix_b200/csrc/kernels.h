@@ -54,6 +54,11 @@ int launch_dye_tables(float* nx, float* ny, Geom dg, int vw, int vh, cudaStream_
 int launch_dye_advect4(const float* din, float* dout, Geom dg, const float2* vel, const uint8_t* obs, Geom vg,
                        const float* nx, const float* ny, float dt, float speed, float diss, int* err, cudaStream_t st);
 
+// ---- frame rendering (render.cu): the demo's field colour map and quiver overlay
+int launch_field_lut(float4* lut, cudaStream_t st);
+int launch_render_frame(const float* dye, const float4* lut, const float2* vel, uint32_t* out, int w, int h, int vw,
+                        int vh, float tile, cudaStream_t st);
+
 // ---- fused pipeline (fused.cu / jacobi_tb.cu) ----------------------------------------------------
 int launch_poisson_mask(const float* pin, const float* div, const uint8_t* nbmask, float* pout,
                         Geom g, int r0, int r1, cudaStream_t st);

@@ -328,12 +328,21 @@ def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
     sim.set_option(L.OPT_TIMING, 1)
     sim.upload("velocity", W.smooth_velocity(w.width, w.height, slab.row0, slab.rows))
 
-    def one_step(k):
+    dye = None
+    if w.dye_size:
+        dye = SlabSmoothParticlesArea(w.dye_size[0], w.dye_size[1], slab)
+        dye.dissipation = w.dye_dissipation
+
+    def one_step(k):                                  # the demo's call order, as workloads.run_step
         for (px, py, r) in w.circles:
             slab.add_circle_obstacle((px, py), r)
         slab.update(W.DT)
+        if dye is not None:
+            dye.update(W.DT)
         for (px, py, vx, vy) in W.orbit_positions(w, k):
             slab.add_velocity((px, py), (vx, vy), w.splat_radius)
+            if dye is not None:
+                dye.add_particles((px, py), w.dye_radius, w.dye_strength)
 
     stream = slab.engine.stream
     step = 0
@@ -409,6 +418,7 @@ def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w.name, "grid": [w.width, w.height], "per_gpu_grid": [w.width, slab.rows],
                        "jacobi_iterations": w.iterations, "obstacles_per_step": len(w.circles),
+                       "dye_grid": list(w.dye_size) if w.dye_size else None,
                        "parallelism": f"row-slabs x{world}, halo {slab.halo} rows, NCCL send/recv"
                                       + (", pressure exchanges overlapped with interior Jacobi" if slab.overlap else ""),
                        "jacobi_depth": depth, "l2": "per-GPU state 4.6 GB exceeds L2; no flush needed",

@@ -132,6 +132,15 @@ class SmoothParticlesArea:
         L.check(self._lib.natrix_dye_export_rgba8(self._handle(), out.ctypes.data_as(C.c_void_p), out.nbytes, 0))
         return out
 
+    def render_frame(self, quiver_tile: float = 0.0) -> np.ndarray:
+        """The frame the demo draws, as an (H, W, 4) uint8 image, top row first: the dye through the plasma / fbm
+        colour map over the clear colour, plus the velocity arrows when ``quiver_tile`` > 0
+        (ref: demo/shaders/demo.FieldFragmentShader.frag, demo.QuiverFragmentShader.frag, simulation_demo.py:249-281)."""
+        out = np.empty((self._rows, self._width, 4), np.uint8)
+        L.check(self._lib.natrix_render_frame(self._handle(), out.ctypes.data_as(C.c_void_p), out.nbytes, 0,
+                                              float(quiver_tile)))
+        return out
+
     def stats(self):
         out = (C.c_double * 4)()
         L.check(self._lib.natrix_dye_stats(self._handle(), out))

@@ -287,6 +287,115 @@ def dye_to_rgba8(dye):
     return np.repeat(c[..., None], 4, axis=-1)
 
 
+# ------------------------------------------------------------------ frame rendering
+def _fract(x):
+    return x - np.floor(x)
+
+
+def field_colour_lut():
+    """plasma(fbm(c)) for the 256 values c = k / 255 an rgba8 texel can take
+    (demo/shaders/demo.FieldFragmentShader.frag:21-33 plasma, :73-92 rand / noise / fbm, :96-99 main).
+    Returns (256, 3) float32.  rand() multiplies sin() by 43758.5, so one ulp of sin() moves a colour by
+    up to ~2/255: comparisons with another sin() implementation need that tolerance."""
+    c = (np.arange(256, dtype=F) / F(255.0)).astype(F)
+
+    def rand(n):
+        return _fract(np.sin(n).astype(F) * F(43758.5453123))
+
+    def noise(p):
+        fl, fc = np.floor(p), _fract(p)
+        return mix(rand(fl), rand(fl + F(1.0)), fc)
+
+    v, a, x = np.zeros_like(c), F(0.5), c.copy()
+    for _ in range(5):
+        v = v + a * noise(x)
+        x = x * F(2.0) + F(100.0)
+        a = a * F(0.5)
+    coeff = np.array([[0.05873234392399702, 0.02333670892565664, 0.5433401826748754],
+                      [2.176514634195958, 0.2383834171260182, 0.7539604599784036],
+                      [-2.689460476458034, -7.455851135738909, 3.110799939717086],
+                      [6.130348345893603, 42.3461881477227, -28.51885465332158],
+                      [-11.10743619062271, -82.66631109428045, 60.13984767418263],
+                      [10.02306557647065, 71.41361770095349, -54.07218655560067],
+                      [-3.658713842777788, -22.93153465461149, 18.19190778539828]], dtype=F)
+    t = v[:, None]
+    out = np.broadcast_to(coeff[6], (256, 3)).astype(F)
+    for k in range(5, -1, -1):
+        out = coeff[k] + t * out
+    return out.astype(F)
+
+
+def _unorm8(c):
+    return np.rint(_clamp(c, F(0.0), F(1.0)) * F(255.0)).astype(F)
+
+
+def _blend8(src_rgb, src_a, dst):
+    """BGFX_STATE_BLEND_ALPHA on an rgba8 target: src * a + dst * (1 - a) per channel, rounded to 8 bits.
+    dst is (H, W, 4) float32 in [0, 1]."""
+    ia = F(1.0) - src_a
+    out = np.empty_like(dst)
+    for ch in range(3):
+        out[..., ch] = _unorm8(src_rgb[..., ch] * src_a + dst[..., ch] * ia) / F(255.0)
+    out[..., 3] = _unorm8(src_a * src_a + dst[..., 3] * ia) / F(255.0)
+    return out
+
+
+def _line(px, py, ax, ay, bx, by):
+    """demo/shaders/demo.QuiverFragmentShader.frag:20-28."""
+    cx, cy = (ax + bx) * F(0.5), (ay + by) * F(0.5)
+    ex, ey = bx - ax, by - ay
+    ln = np.sqrt(ex * ex + ey * ey)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        dx, dy = ex / ln, ey / ln
+    rx, ry = px - cx, py - cy
+    d1 = np.abs(rx * dy + ry * (-dx))
+    d2 = np.abs(rx * dx + ry * dy) - F(0.5) * ln
+    return np.maximum(d1, d2)
+
+
+def render_frame(dye, vel=None, quiver_tile=0.0):
+    """The frame demo/simulation_demo.py:249-281 draws, as (H, W, 4) uint8, top row first.
+
+    Pass 1: the rgba8 dye texture (dye_to_rgba8) through plasma(fbm(texel)) with alpha = texel
+    (demo.FieldFragmentShader.frag:96-99), alpha-blended over the clear colour 0x1a0427ff (:94).
+    Pass 2 (quiver_tile > 0): demo.QuiverFragmentShader.frag:14-70, white arrows with alpha = 1 - dist.
+    Conventions as in natrix_b200/csrc/render.cu: the quad covers the framebuffer, which has the dye grid's
+    size; framebuffer y grows upwards (dye row 0 at the bottom); each pass is rounded to 8 bits."""
+    h, w = dye.shape
+    c8 = dye_to_rgba8(dye)[..., 0].astype(np.int64)
+    lut = field_colour_lut()
+    dst = np.empty((h, w, 4), F)
+    dst[...] = np.array([26.0, 4.0, 39.0, 255.0], F) / F(255.0)
+    fb = _blend8(lut[c8], (c8.astype(F) / F(255.0)).astype(F), dst)           # indexed by framebuffer row (bottom = 0)
+    if quiver_tile > 0:
+        t = F(quiver_tile)
+        vh, vw = vel.shape[:2]
+        fx = (np.arange(w, dtype=F) + F(0.5))[None, :] + np.zeros((h, 1), F)
+        fy = (np.arange(h, dtype=F) + F(0.5))[:, None] + np.zeros((1, w), F)
+        cx, cy = (np.floor(fx / t) + F(0.5)) * t, (np.floor(fy / t) + F(0.5)) * t
+        qx = (F(1.0) - cx / F(w)) * F(vw)
+        qy = (F(1.0) - cy / F(h)) * F(vh)
+        tx, ty, bx, by, dx, dy = _bilinear_corners(qx, qy, vw, vh)
+        h1x = mix(vel[ty, bx, 0], vel[ty, tx, 0], dx)
+        h2x = mix(vel[by, bx, 0], vel[by, tx, 0], dx)
+        vx = F(-1.0) * mix(h2x, h1x, dy) * (F(w) / F(vw))
+        vy = F(-1.0) * vel[by, bx, 1] * (F(h) / F(vh))       # mix(a, b, vec2(t, 0)): y is never interpolated
+        vx, vy = vx * t * F(0.4), vy * t * F(0.4)
+        px, py = fx - cx, fy - cy
+        mag = np.sqrt(vx * vx + vy * vy)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            ux, uy = vx / mag, vy / mag
+        m2 = _clamp(mag, F(0.0), t * F(0.5))
+        ax, ay = ux * m2, uy * m2
+        shaft = _line(px, py, ax, ay, -ax, -ay)
+        hd1 = _line(px, py, ax, ay, F(0.4) * ax + F(0.2) * (-ay), F(0.4) * ay + F(0.2) * ax)
+        hd2 = _line(px, py, ax, ay, F(0.4) * ax + F(0.2) * ay, F(0.4) * ay + F(0.2) * (-ax))
+        dist = np.where(mag > F(0.001), np.minimum(shaft, np.minimum(hd1, hd2)), F(1.0)).astype(F)
+        white = np.ones((h, w, 3), F)
+        fb = _blend8(white, F(1.0) - _clamp(dist, F(0.0), F(1.0)), fb)
+    return np.rint(fb[::-1] * F(255.0)).astype(np.uint8)
+
+
 # ------------------------------------------------------------------ simulator mirror
 class OracleFluidSimulator:
     """State machine of natrix/core/fluid_simulator.py:15-515 over NumPy arrays.

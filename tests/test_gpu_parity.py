@@ -337,6 +337,32 @@ def test_dye_rgba8_export_vs_oracle():
     assert np.array_equal(img, dye_to_rgba8(dye))
 
 
+FRAME_TOL = 2      # 8-bit levels: rand() = fract(sin(n) * 43758.5) amplifies one ulp of sin() to ~2/255 of colour
+
+
+@pytest.mark.parametrize("tile", [0.0, 8.0, 32.0])
+def test_render_frame_vs_oracle(tile):
+    """the demo's frame (field colour map over the clear colour, optional quiver overlay)
+    against the NumPy transcription of the two fragment shaders, after a few demo steps."""
+    from oracle.natrix_oracle import render_frame
+
+    w = W.demo_workload()
+    sim, dye = W.build(w, FluidSimulator, SmoothParticlesArea)
+    for k in range(6):
+        W.run_step(w, sim, dye, k)
+    dye.add_particles((0.3, 0.6), 120.0, 0.8)                   # pending splat: the frame must include it
+    img = dye.render_frame(tile)
+    ref = render_frame(dye.download(), sim.download("velocity"), tile)
+    assert img.shape == (w.dye_size[1], w.dye_size[0], 4) and img.dtype == np.uint8
+    diff = np.abs(img.astype(np.int32) - ref.astype(np.int32))
+    assert float((diff > FRAME_TOL).mean()) < 1e-4, f"{int((diff > FRAME_TOL).sum())} channel values off by more than {FRAME_TOL}"
+    assert int(diff.max()) <= 16                                # an arrow edge may flip a pixel's coverage by one rounding
+    if tile == 0.0:
+        bg = dye.download()[::-1] <= 0.0                       # no dye: exactly the clear colour 0x1a0427ff
+        assert bg.any() and (img[bg] == np.array([26, 4, 39, 255], np.uint8)).all()
+    assert len(np.unique(img.reshape(-1, 4), axis=0)) > 50     # not a constant image
+
+
 def test_config5_slab_size_fused_equals_reference_order_pipeline():
     """config 5 at its per-GPU size (32768 x 4096, 64 circles): tile planner, select / solid / free bodies
     and the fused pre-projection against the one-kernel-per-shader pipeline, bit for bit (24 sweeps)."""
@@ -352,3 +378,12 @@ def test_config5_slab_size_fused_equals_reference_order_pipeline():
         assert np.array_equal(fa, fb), f"{name}: {int(np.count_nonzero(fa != fb))} cells differ"
         assert float(np.abs(fa).max()) > 0.0
         del fa, fb
+
+
+def test_headless_demo_writes_frames(tmp_path):
+    """the headless replay of the demo loop produces PNG frames that are not blank."""
+    from natrix_b200.headless_demo import run
+
+    written, fps = run(12, 6, tmp_path, quiver=32.0, width=640, height=360)
+    assert [p.name for p in written] == ["frame_00006.png", "frame_00012.png"] and fps > 0
+    assert all(p.stat().st_size > 2000 for p in written)

@@ -62,3 +62,31 @@ def test_smooth_velocity_slab_equals_window_of_full_field():
     part = W.smooth_velocity(128, 96, row0=32, rows=40)
     assert np.array_equal(full[32:72], part)
     assert np.max(np.abs(full)) <= 0.5
+
+
+def test_png_writer_round_trip(tmp_path):
+    """headless demo driver: the RGBA8 PNG it writes decodes back to the same pixels."""
+    import struct
+    import zlib
+
+    from natrix_b200.headless_demo import write_png
+
+    img = np.random.default_rng(1).integers(0, 256, (37, 53, 4), dtype=np.uint8)
+    path = tmp_path / "t.png"
+    write_png(path, img)
+    b = path.read_bytes()
+    assert b[:8] == b"\x89PNG\r\n\x1a\n"
+    i, idat, tags = 8, b"", []
+    while i < len(b):
+        n, = struct.unpack(">I", b[i:i + 4])
+        tag, data = b[i + 4:i + 8], b[i + 8:i + 8 + n]
+        assert struct.unpack(">I", b[i + 8 + n:i + 12 + n])[0] == zlib.crc32(tag + data) & 0xFFFFFFFF
+        tags.append(tag)
+        if tag == b"IHDR":
+            assert struct.unpack(">IIBBBBB", data) == (53, 37, 8, 6, 0, 0, 0)
+        if tag == b"IDAT":
+            idat += data
+        i += 12 + n
+    assert tags[0] == b"IHDR" and tags[-1] == b"IEND"
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(37, 1 + 53 * 4)
+    assert (raw[:, 0] == 0).all() and np.array_equal(raw[:, 1:].reshape(37, 53, 4), img)
