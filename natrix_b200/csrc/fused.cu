@@ -99,16 +99,31 @@ k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, fl
         W0[j] = W1[j] = 0.0f;
     }
 
+    // The centre cells of a row (obstacle word + 4 velocities) are the only loads that miss to DRAM - the
+    // back-trace gathers land on rows this warp has just streamed through.  They are fetched one row ahead
+    // so that their latency overlaps the arithmetic of the current row.
+    uint32_t ow_n = 0u;
+    float4 c01_n = make_float4(0.0f, 0.0f, 0.0f, 0.0f), c23_n = c01_n;
+    auto fetch_row = [&](int ly_) {
+        const int gy_ = g.y0 + ly_;
+        if (gy_ >= 0 && gy_ < g.hg && ly_ < out_hi + DEPTH) {
+            const ptrdiff_t base = lin(g, xc0, ly_);
+            ow_n = *reinterpret_cast<const uint32_t*>(obs + base);
+            c01_n = *reinterpret_cast<const float4*>(vin + base);
+            c23_n = *reinterpret_cast<const float4*>(vin + base + 2);
+        }
+    };
+    fetch_row(out_lo - DEPTH);
+
     for (int ly = out_lo - DEPTH; ly < out_hi + DEPTH; ++ly) {
         const int gy = g.y0 + ly;
         // ---- stage 0: advect row ly (ref: shader.AdvectVelocity.comp:27-50).  All 4 cells are traced
         // without branching (16 independent gathers in flight); solid cells are zeroed afterwards.
         float2 An[4];
+        const uint32_t ow = ow_n;
+        const float4 c01 = c01_n, c23 = c23_n;
+        fetch_row(ly + 1);
         if (gy >= 0 && gy < g.hg) {
-            const ptrdiff_t base = lin(g, xc0, ly);
-            const uint32_t ow = *reinterpret_cast<const uint32_t*>(obs + base);
-            const float4 c01 = *reinterpret_cast<const float4*>(vin + base);
-            const float4 c23 = *reinterpret_cast<const float4*>(vin + base + 2);
             const float2 cv[4] = {make_float2(c01.x, c01.y), make_float2(c01.z, c01.w), make_float2(c23.x, c23.y),
                                   make_float2(c23.z, c23.w)};
 #pragma unroll
