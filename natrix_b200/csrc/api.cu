@@ -242,7 +242,7 @@ int check_range_flag(natrix_sim* s, bool wait) {
             if (*s->h_err) {
                 *s->h_err = 0;
                 CU(cudaMemsetAsync(s->d_err, 0, sizeof(int), s->st));
-                return fail(NATRIX_ERR_RANGE, "advection back-trace left the slab's halo rows; enlarge halo");
+                return fail(NATRIX_ERR_RANGE, "a back-trace (velocity or dye advection) left the slab's halo rows; enlarge the halo");
             }
         } else if (q != cudaErrorNotReady) {
             CU(q);
@@ -713,7 +713,7 @@ int natrix_halo_rows_needed(natrix_sim* s, int phase, float dt) {
         return (int)reach + 4;
     }
     case 1: return 0;                 // phase 0 already produced rows ext(4)
-    case 2: return s->jacobi_depth;
+    case 2: return s->jacobi_depth;   // per launch; a group of k launches between two exchanges needs k times that
     case 3: return 1;
     default: return fail(NATRIX_ERR_ARG, "phase must be 0..3");
     }

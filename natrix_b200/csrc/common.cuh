@@ -119,13 +119,7 @@ __device__ __forceinline__ float bitsel(float a, float b, uint32_t m) {
     return __uint_as_float((__float_as_uint(a) & m) | (__float_as_uint(b) & ~m));
 }
 
-// streaming global accesses: data touched once per kernel should not pollute L1
-__device__ __forceinline__ float4 ldg_stream(const float4* p) {
-    float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
+// streaming stores: data written once per kernel should not pollute L1
 __device__ __forceinline__ void stg_stream(float4* p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");

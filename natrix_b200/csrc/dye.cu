@@ -12,7 +12,9 @@ constexpr int BX = 64, BY = 4, BT = BX * BY;   // 2-D blocks: back-traced gather
 // [y0, y0 + hl) plus `halo` rows either side), vg the simulator's velocity rows.  Arrays are indexed by
 // local row; the arithmetic only ever sees GLOBAL cell coordinates, so a slab reproduces the full grid.
 // A gather that leaves the held rows raises *err (slabs only: the full grid cannot trip it).
+template <bool SLAB = true>
 __device__ __forceinline__ int held_row(const Geom& g, int gy, int* __restrict__ err) {
+    if (!SLAB) return gy;                        // full grid: y0 = 0 and every clamped row is held
     const int lo = g.y0 - g.halo, hi = g.y0 + g.hl + g.halo - 1;
     if (gy < lo || gy > hi) {
         *err = 1;
@@ -84,6 +86,7 @@ __global__ void k_dye_tables(float* __restrict__ nx, float* __restrict__ ny, con
     if (i < dg.hl) ny[i] = ((float)(i + dg.y0) / (float)dg.hg) * (float)vh;
 }
 
+template <bool SLAB>
 __global__ void __launch_bounds__(D4X * D4Y)
 k_dye_advect4(const float* __restrict__ din, float* __restrict__ dout, const Geom dg, const float2* __restrict__ vel,
               const uint8_t* __restrict__ obs, const Geom vg, const float* __restrict__ nxt,
@@ -98,9 +101,9 @@ k_dye_advect4(const float* __restrict__ din, float* __restrict__ dout, const Geo
     const float my = (float)(vh - 1), mx = (float)(vw - 1);
     const int vty = (int)clampf(ceilf(ny), 0.0f, my), vby = (int)clampf(floorf(ny), 0.0f, my);
     const float vdy = ny - (float)vby;
-    const float2* vrow_t = vel + lin(vg, 0, held_row(vg, vty, err));
-    const float2* vrow_b = vel + lin(vg, 0, held_row(vg, vby, err));
-    const uint8_t* orow = obs + lin(vg, 0, held_row(vg, (int)(unsigned)ny, err));
+    const float2* vrow_t = vel + lin(vg, 0, held_row<SLAB>(vg, vty, err));
+    const float2* vrow_b = vel + lin(vg, 0, held_row<SLAB>(vg, vby, err));
+    const uint8_t* orow = obs + lin(vg, 0, held_row<SLAB>(vg, (int)(unsigned)ny, err));
     const float4 nx4 = *reinterpret_cast<const float4*>(nxt + x0);       // pw % 4 == 0
     const float nxs[4] = {nx4.x, nx4.y, nx4.z, nx4.w};
     float out[4];
@@ -115,8 +118,8 @@ k_dye_advect4(const float* __restrict__ din, float* __restrict__ dout, const Geo
         const float fx = (float)(x0 + j) - vx * dt * speed;
         const float fy = (float)gy - vy * dt * speed;
         const Corners q = corners(fx, fy, pw, ph);
-        const float* drow_t = din + lin(dg, 0, held_row(dg, q.ty, err));
-        const float* drow_b = din + lin(dg, 0, held_row(dg, q.by, err));
+        const float* drow_t = din + lin(dg, 0, held_row<SLAB>(dg, q.ty, err));
+        const float* drow_b = din + lin(dg, 0, held_row<SLAB>(dg, q.by, err));
         const float g1 = mixf(drow_t[q.bx], drow_t[q.tx], q.dx);
         const float g2 = mixf(drow_b[q.bx], drow_b[q.tx], q.dx);
         const float r = mixf(g2, g1, q.dy) * diss;
@@ -164,7 +167,10 @@ int launch_dye_advect4(const float* din, float* dout, Geom dg, const float2* vel
     // _ParticleSize / _VelocitySize (:34): IEEE single division, same on host and device
     const float rx = (float)dg.w / (float)vg.w, ry = (float)dg.hg / (float)vg.hg;
     dim3 grid((dg.w / 4 + D4X - 1) / D4X, (dg.hl + D4Y - 1) / D4Y, 1);
-    k_dye_advect4<<<grid, dim3(D4X, D4Y, 1), 0, st>>>(din, dout, dg, vel, obs, vg, nx, ny, rx, ry, dt, speed, diss, err);
+    if (dg.hl == dg.hg && vg.hl == vg.hg)
+        k_dye_advect4<false><<<grid, dim3(D4X, D4Y, 1), 0, st>>>(din, dout, dg, vel, obs, vg, nx, ny, rx, ry, dt, speed, diss, err);
+    else
+        k_dye_advect4<true><<<grid, dim3(D4X, D4Y, 1), 0, st>>>(din, dout, dg, vel, obs, vg, nx, ny, rx, ry, dt, speed, diss, err);
     return 1;
 }
 

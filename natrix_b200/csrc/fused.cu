@@ -337,16 +337,37 @@ k_splat_dye_boxes(float* __restrict__ dye, const Geom dg, const __grid_constant_
 
 // ref: shader.AddCircleObstacle.comp:24-36 for up to MAX_CIRCLES queued circles in one launch, each on
 // its own bounding box (blockIdx.z); overlapping circles store the same value.
-struct CircleBoxes { int n; float sx[MAX_CIRCLES], sy[MAX_CIRCLES], r[MAX_CIRCLES]; Box b[MAX_CIRCLES]; };
-__global__ void __launch_bounds__(SBX * SBY)
+struct CircleBoxes { int n; float sx[MAX_CIRCLES], sy[MAX_CIRCLES], r[MAX_CIRCLES]; Box b[MAX_CIRCLES]; int first[MAX_CIRCLES + 1]; };
+constexpr int CBX = 32, CBY = 8, CCELLS = 4;     // a block covers 128 x 8 cells, 4 consecutive cells per thread
+// Blocks are numbered circle by circle (first[i] = first block of circle i), so the grid holds exactly the
+// blocks the bounding boxes need whatever the mix of radii.
+__global__ void __launch_bounds__(CBX * CBY)
 k_add_circles(uint8_t* __restrict__ obs, const Geom g, const __grid_constant__ CircleBoxes c) {
-    const int i = blockIdx.z;
+    int i = 0;
+    while (i + 1 < c.n && (int)blockIdx.x >= c.first[i + 1]) ++i;
     const Box bx = c.b[i];
-    const int x = bx.x0 + blockIdx.x * SBX + threadIdx.x;
-    const int gy = bx.y0 + blockIdx.y * SBY + threadIdx.y;
+    const int xa = bx.x0 & ~3;                                   // 4-cell groups aligned in x
+    const int bw = (bx.x1 - xa + CBX * CCELLS - 1) / (CBX * CCELLS);
+    const int lb = (int)blockIdx.x - c.first[i];
+    const int x = xa + ((lb % bw) * CBX + threadIdx.x) * CCELLS;
+    const int gy = bx.y0 + (lb / bw) * CBY + threadIdx.y;
     if (x >= bx.x1 || gy >= bx.y1) return;
-    const float ex = c.sx[i] - (float)x, ey = c.sy[i] - (float)gy;
-    if (sqrtf(ex * ex + ey * ey) <= c.r[i]) obs[lin(g, x, gy - g.y0)] = OBS_DYNAMIC;
+    const float ey = c.sy[i] - (float)gy, r = c.r[i];
+    uint32_t in = 0u;
+#pragma unroll
+    for (int j = 0; j < CCELLS; ++j) {
+        const float ex = c.sx[i] - (float)(x + j);
+        if (x + j >= bx.x0 && x + j < bx.x1 && sqrtf(ex * ex + ey * ey) <= r) in |= 1u << j;
+    }
+    if (!in) return;
+    uint8_t* row = obs + lin(g, x, gy - g.y0);
+    if (in == 0xfu && (reinterpret_cast<uintptr_t>(row) & 3u) == 0) {
+        *reinterpret_cast<uint32_t*>(row) = OBS_DYNAMIC * 0x01010101u;
+    } else {
+#pragma unroll
+        for (int j = 0; j < CCELLS; ++j)
+            if (in & (1u << j)) row[j] = OBS_DYNAMIC;
+    }
 }
 
 // Cells with sqrt(ex^2 + ey^2) <= r lie within r + 2 of the centre along each axis (sqrt is monotone and
@@ -543,18 +564,22 @@ int launch_splat_velocity_boxes(float2* vel, Geom g, int r0, int r1, const Splat
 
 int launch_add_circles(uint8_t* obs, Geom g, int r0, int r1, const float* sxyr, int n, cudaStream_t st) {
     int launched = 0;
-    for (int base = 0; base < n; base += MAX_CIRCLES) {
+    for (int base = 0; base < n;) {
         CircleBoxes c;
         c.n = 0;
-        for (int i = base; i < n && c.n < MAX_CIRCLES; ++i) {
+        c.first[0] = 0;
+        int i = base;
+        for (; i < n && c.n < MAX_CIRCLES; ++i) {
             const Box b = splat_box(sxyr[3 * i], sxyr[3 * i + 1], sxyr[3 * i + 2], 0, g.w, g.y0 + r0, g.y0 + r1);
             if (b.x1 <= b.x0) continue;
             c.sx[c.n] = sxyr[3 * i]; c.sy[c.n] = sxyr[3 * i + 1]; c.r[c.n] = sxyr[3 * i + 2]; c.b[c.n] = b;
+            const int bw = (b.x1 - (b.x0 & ~3) + CBX * CCELLS - 1) / (CBX * CCELLS), bh = (b.y1 - b.y0 + CBY - 1) / CBY;
+            c.first[c.n + 1] = c.first[c.n] + bw * bh;
             ++c.n;
         }
-        const dim3 grid = boxes_grid(c);
-        if (c.n == 0 || grid.x == 0 || grid.y == 0) continue;
-        k_add_circles<<<grid, dim3(SBX, SBY, 1), 0, st>>>(obs, g, c);
+        base = i;
+        if (c.n == 0 || c.first[c.n] == 0) continue;
+        k_add_circles<<<c.first[c.n], dim3(CBX, CBY, 1), 0, st>>>(obs, g, c);
         ++launched;
     }
     return launched;
