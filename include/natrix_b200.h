@@ -61,7 +61,8 @@ enum natrix_option {
                                 1 = fused / temporally blocked kernels (default)            */
     NATRIX_OPT_JACOBI_DEPTH = 1, /* sweeps per launch of the temporally blocked Jacobi kernel */
     NATRIX_OPT_TIMING = 2,   /* 1 = record per-stage CUDA events (natrix_get_timings)        */
-    NATRIX_OPT_RESERVED = 3, /* unused (kept so that the ids below stay stable)                */
+    NATRIX_OPT_WARM_START = 3, /* NOT reference behaviour, default 0: 1 = keep the previous
+                                step's pressure as the initial guess instead of clearing it            */
     NATRIX_OPT_PACKED = 4    /* 1 = f32x2 packed arithmetic in the Jacobi kernel              */
 };
 

@@ -242,6 +242,17 @@ class FluidSimulator:
         L.check(self._lib.natrix_get_option(self._handle(), int(option), C.byref(out)))
         return out.value
 
+    @property
+    def warm_start(self) -> bool:
+        """NOT reference behaviour (default False): keep the previous step's pressure as the Jacobi initial
+        guess instead of clearing it (fluid_simulator.py:236-248), so that fewer iterations reach the same
+        residual."""
+        return bool(self.get_option(L.OPT_WARM_START))
+
+    @warm_start.setter
+    def warm_start(self, value: bool):
+        self.set_option(L.OPT_WARM_START, 1 if value else 0)
+
     def _shape(self, fid: int):
         comps = L.FIELD_COMPONENTS[fid]
         return (self._rows, self._width, comps) if comps > 1 else (self._rows, self._width)

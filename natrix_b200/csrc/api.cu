@@ -56,13 +56,14 @@ struct natrix_sim {
     float alpha = (float)(1.0 / 0.1), rbeta = (float)(1.0 / (4.0 + 1.0 / 0.1));
     int iterations = 50, has_borders = 1, viscous = 1;
     // options
-    int pipeline = 1, jacobi_depth = 8, timing = 0, packed = 1;
+    int pipeline = 1, jacobi_depth = 8, timing = 0, packed = 1, warm_start = 0;
     // bookkeeping
     std::vector<SplatV> pending;                 // add_velocity calls not yet applied (pipeline 1)
     std::vector<float> circles;                  // queued add_circle_obstacle calls (sx, sy, r), pipeline 1
     std::vector<int> heavy;                      // merged [lo, hi) local-row intervals stamped with obstacles this step
     std::vector<int> boxes;                      // (x0, x1, y0, y1) per obstacle stamped this step (scheduling hint)
     bool obs_dirty = false, p_is_zero = false, fused_pre = false;
+    bool first_block = false;                    // no Jacobi launch of this step has been queued yet
     int* d_err = nullptr;                        // [0] advection left the slab's halo; [1..] per band of OVER_BAND
                                                  // rows: some |v| > 1 in the READ velocity
     int nbands = 0;
@@ -288,15 +289,17 @@ int phase_advect(natrix_sim* s, float dt) {
 int phase_forces(natrix_sim* s, float dt) {
     const Geom& g = s->g;
     stamp(s, ST_VORT);
+    s->first_block = true;
     if (s->fused_pre) {
         stamp(s, ST_DIV);
         // clear pressure (fluid_simulator.py:236-248): the first temporally blocked launch treats p as
-        // zero without reading it, so the fill itself is only needed for the 1-sweep fallback kernel
-        if (!jacobi_tb_supported(g)) {
+        // zero without reading it, so the fill itself is only needed for the 1-sweep fallback kernel.
+        // NATRIX_OPT_WARM_START keeps the previous step's pressure as the initial guess instead.
+        if (!s->warm_start && !jacobi_tb_supported(g)) {
             CU(cudaMemsetAsync(s->p_base[s->pr], 0, s->cells_alloc * sizeof(float), s->st));
             s->launches += 1;
         }
-        s->p_is_zero = true;
+        s->p_is_zero = !s->warm_start;
         return 0;
     }
     s->launches += launch_vorticity(s->vel[s->vr], s->vort, g, s->ext_lo(3), s->ext_hi(3), s->st);
@@ -312,9 +315,11 @@ int phase_forces(natrix_sim* s, float dt) {
     s->launches += launch_divergence(s->vel[s->vr], s->obs, s->div, s->nbm, g, 0, g.hl, s->st);
     // clear pressure (fluid_simulator.py:236-248); halo rows included so the first Jacobi
     // block needs no exchange
-    CU(cudaMemsetAsync(s->p_base[s->pr], 0, s->cells_alloc * sizeof(float), s->st));
-    s->launches += 1;
-    s->p_is_zero = true;
+    if (!s->warm_start) {
+        CU(cudaMemsetAsync(s->p_base[s->pr], 0, s->cells_alloc * sizeof(float), s->st));
+        s->launches += 1;
+    }
+    s->p_is_zero = !s->warm_start;
     CU(cudaGetLastError());
     return 0;
 }
@@ -611,6 +616,7 @@ int natrix_set_option(natrix_sim* s, int option, int value) {
         s->jacobi_depth = value; return 0;
     case NATRIX_OPT_TIMING: s->timing = value ? 1 : 0; return 0;
     case NATRIX_OPT_PACKED: s->packed = value ? 1 : 0; return 0;
+    case NATRIX_OPT_WARM_START: s->warm_start = value ? 1 : 0; return 0;
     default: return fail(NATRIX_ERR_ARG, "unknown option id");
     }
 }
@@ -622,6 +628,7 @@ int natrix_get_option(natrix_sim* s, int option, int* value) {
     case NATRIX_OPT_JACOBI_DEPTH: *value = s->jacobi_depth; return 0;
     case NATRIX_OPT_TIMING: *value = s->timing; return 0;
     case NATRIX_OPT_PACKED: *value = s->packed; return 0;
+    case NATRIX_OPT_WARM_START: *value = s->warm_start; return 0;
     default: return fail(NATRIX_ERR_ARG, "unknown option id");
     }
 }
@@ -688,7 +695,8 @@ int natrix_step_phase(natrix_sim* s, int phase, float dt, int sweeps) {
     case 1: return phase_forces(s, dt);
     case 2:
         NEED(sweeps > 0, "sweeps must be positive");
-        if (s->p_is_zero) stamp(s, ST_JACOBI);       // first block of the step: the stage spans all blocks + exchanges
+        if (s->first_block) stamp(s, ST_JACOBI);     // first block of the step: the stage spans all blocks + exchanges
+        s->first_block = false;
         return phase_jacobi(s, sweeps);
     case 3: {
         if (int rc = phase_project(s)) return rc;
@@ -696,7 +704,8 @@ int natrix_step_phase(natrix_sim* s, int phase, float dt, int sweeps) {
     }
     case 4:
         NEED(sweeps > 0, "sweeps must be positive");
-        if (s->p_is_zero) stamp(s, ST_JACOBI);
+        if (s->first_block) stamp(s, ST_JACOBI);
+        s->first_block = false;
         return phase_jacobi_interior(s, sweeps);
     case 5: return phase_jacobi_edges(s, sweeps);
     default: return fail(NATRIX_ERR_ARG, "phase must be 0..5");

@@ -191,7 +191,9 @@ class SlabSimulator:
             if overlap:
                 e.phase(4, time_delta, t)                     # interior rows: no halo needed
             if i == 0:
-                self.exchange(("divergence", "nbmask"), min(span, n), comm=overlap)
+                # p starts at zero, halos included - unless the simulator warm-starts from the last step's pressure
+                warm = bool(getattr(self.sim, "warm_start", False))
+                self.exchange(("divergence", "nbmask") + (("pressure",) if warm else ()), min(span, n), comm=overlap)
             else:
                 self.exchange("pressure", t, comm=overlap)
             e.phase(5 if overlap else 2, time_delta, t)       # edge rows (or all rows) after the exchange

@@ -476,7 +476,8 @@ class OracleFluidSimulator:
             self._vel[self.VELOCITY_WRITE] = viscosity_sweep(self.velocity, alpha, rbeta)
             self._flip_v()
         self.divergence = divergence(self.velocity, self.obstacles)             # :231-233
-        self._p[self.PRESSURE_READ] = np.zeros_like(self._p[0])                 # :236-248
+        if not getattr(self, "warm_start", False):      # warm_start: opt-in extension of the product, not the reference
+            self._p[self.PRESSURE_READ] = np.zeros_like(self._p[0])             # :236-248
         nb = neighbours(solid(self.obstacles))
         for _ in range(int(self.iterations)):                                   # :251-255
             self._p[self.PRESSURE_WRITE] = poisson_sweep(

@@ -21,6 +21,7 @@ from natrix_b200.slabs import SlabSimulator, SlabSmoothParticlesArea  # noqa: E4
 from natrix_b200.smooth_particles_area import SmoothParticlesArea  # noqa: E402
 
 width, height, steps, iters = (int(a) for a in (sys.argv[1:5] + ["1024", "2048", "3", "37"][len(sys.argv) - 1:]))
+warm = len(sys.argv) > 5 and sys.argv[5] == "warm"        # NATRIX_OPT_WARM_START on both sides
 rank, world, local = (int(os.environ.get(k, "0")) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -37,6 +38,7 @@ for pipeline in (1, 0):
     slab.sim.set_option(L.OPT_PIPELINE, pipeline)
     for s in (ref, slab.sim):
         s.vorticity, s.viscosity, s.iterations = 1.0, (0.3 if pipeline else 0.0), iters
+        s.warm_start = warm
     slab.iterations = iters
     ref.upload("velocity", v0)
     slab.sim.upload("velocity", v0[slab.row0:slab.row0 + slab.rows])

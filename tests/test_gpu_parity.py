@@ -387,3 +387,45 @@ def test_headless_demo_writes_frames(tmp_path):
     written, fps = run(12, 6, tmp_path, quiver=32.0, width=640, height=360)
     assert [p.name for p in written] == ["frame_00006.png", "frame_00012.png"] and fps > 0
     assert all(p.stat().st_size > 2000 for p in written)
+
+
+@pytest.mark.parametrize("pipeline", [0, 1])
+def test_warm_start_option_vs_oracle(pipeline):
+    """NATRIX_OPT_WARM_START (not reference behaviour): the pressure of the previous step is the
+    initial guess; still bit-identical to the oracle run with the pressure clear skipped, and different from the
+    reference-order run."""
+    w = W.cfg2_workload()
+    w.width, w.height, w.iterations = 384, 256, 21
+    g, _ = W.build(w, _sim_cls(pipeline), None)
+    o, _ = W.build(w, OracleFluidSimulator, None)
+    cold, _ = W.build(w, _sim_cls(pipeline), None)
+    g.warm_start = True
+    o.warm_start = True
+    assert g.warm_start and not cold.warm_start
+    for k in range(4):
+        for s in (g, o, cold):
+            W.run_step(w, s, None, k)
+        assert_fields_close(W.fields_of(g), W.fields_of(o), f"step {k}: ", exact=True)
+    assert not np.array_equal(g.download("pressure"), cold.download("pressure"))
+
+
+def test_checkpoint_restores_a_run_bit_identically(tmp_path):
+    """natrix_b200.checkpoint through the C ABI: velocity, pressure, pending obstacles, parameters and the dye."""
+    from natrix_b200 import checkpoint
+
+    w = W.demo_workload()
+    w.init = "random"
+    a, ad = W.build(w, FluidSimulator, SmoothParticlesArea)
+    for k in range(4):
+        W.run_step(w, a, ad, k)
+    a.add_circle_obstacle((0.3, 0.6), 25.0)
+    a.add_triangle_obstacle((0.6, 0.2), (0.8, 0.3), (0.7, 0.6), True)
+    checkpoint.save(tmp_path / "c.npz", a, [ad])
+    b, bd = W.build(w, FluidSimulator, SmoothParticlesArea)
+    b.iterations = 3
+    checkpoint.load(tmp_path / "c.npz", b, [bd])
+    assert b.iterations == a.iterations
+    for k in range(4, 7):
+        W.run_step(w, a, ad, k)
+        W.run_step(w, b, bd, k)
+    assert_fields_close(W.fields_of(a, ad), W.fields_of(b, bd), "after restore: ", exact=True)

@@ -90,3 +90,34 @@ def test_png_writer_round_trip(tmp_path):
     assert tags[0] == b"IHDR" and tags[-1] == b"IEND"
     raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(37, 1 + 53 * 4)
     assert (raw[:, 0] == 0).all() and np.array_equal(raw[:, 1:].reshape(37, 53, 4), img)
+
+
+def test_checkpoint_round_trip_continues_bit_identically(tmp_path):
+    """natrix_b200.checkpoint on the oracle classes: a run restored from a file written after 3 frames
+    (with an obstacle stamped and not yet consumed) continues exactly like the run that never stopped."""
+    from natrix_b200 import checkpoint
+    from oracle.natrix_oracle import OracleFluidSimulator, OracleSmoothParticlesArea
+
+    def make():
+        w = W.demo_workload()
+        w.width, w.height, w.dye_size, w.iterations, w.init = 48, 36, (96, 72), 7, "random"
+        return (w, *W.build(w, OracleFluidSimulator, OracleSmoothParticlesArea))
+
+    w, a, ad = make()
+    for k in range(3):
+        W.run_step(w, a, ad, k)
+    a.add_circle_obstacle((0.3, 0.6), 5.0)                      # pending obstacle: part of the state
+    checkpoint.save(tmp_path / "c.npz", a, [ad])
+    _, b, bd = make()
+    b.iterations, b.vorticity = 3, 9.0                          # overwritten by the checkpoint
+    checkpoint.load(tmp_path / "c.npz", b, [bd])
+    assert (b.iterations, b.vorticity, b.viscosity) == (a.iterations, a.vorticity, a.viscosity)
+    for k in range(3, 6):
+        W.run_step(w, a, ad, k)
+        W.run_step(w, b, bd, k)
+    for name in ("velocity", "pressure", "divergence"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    assert np.array_equal(ad.particles, bd.particles)
+    _, c, cd = make()
+    with pytest.raises(ValueError):
+        checkpoint.load(tmp_path / "c.npz", c, [])              # dye count mismatch
