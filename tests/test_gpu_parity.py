@@ -429,3 +429,44 @@ def test_checkpoint_restores_a_run_bit_identically(tmp_path):
         W.run_step(w, a, ad, k)
         W.run_step(w, b, bd, k)
     assert_fields_close(W.fields_of(a, ad), W.fields_of(b, bd), "after restore: ", exact=True)
+
+
+def test_pure_c_host_matches_the_python_mirror():
+    """examples/c_host.c drives the demo loop through the C ABI with no Python in the process; the field
+    statistics it prints equal those of the same loop through the ctypes mirror."""
+    import ctypes
+    import subprocess
+
+    exe = ROOT / "examples" / "_build" / "c_host"
+    if not exe.exists():
+        pytest.skip("examples/_build/c_host is not built (python -c 'import __graft_entry__ as g; g.build()')")
+    frames = 12
+    out = subprocess.run([str(exe), str(frames)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    got = {ln.split()[0]: [float(v) for v in ln.split()[1:]] for ln in out.stdout.splitlines()
+           if ln.split()[0] in ("velocity", "pressure", "dye")}
+
+    libm = ctypes.CDLL("libm.so.6")
+    for fn in (libm.cosf, libm.sinf):
+        fn.restype, fn.argtypes = ctypes.c_float, [ctypes.c_float]
+    f32 = np.float32
+    sim = FluidSimulator(640, 360, None)
+    sim.vorticity, sim.viscosity, sim.iterations = 1.0, 0.5, 50
+    dye = SmoothParticlesArea(1280, 720, sim, None)
+    dye.dissipation = 0.98
+    dt = float(f32(1.0) / f32(60.0))
+
+    def pos(k):
+        a = float(f32(0.1) * f32(k))
+        return f32(0.5) + f32(0.3) * f32(libm.cosf(a)), f32(0.5) + f32(0.3) * f32(libm.sinf(a))
+
+    for k in range(frames):
+        sim.add_circle_obstacle((0.5, 0.5), 40.0)
+        sim.update(dt)
+        dye.update(dt)
+        (x1, y1), (x0, y0) = pos(k), pos(k - 1)
+        sim.add_velocity((float(x1), float(y1)), (float(f32(10.0) * (x1 - x0)), float(f32(10.0) * (y1 - y0))), 32.0)
+        dye.add_particles((float(x1), float(y1)), 250.0, 0.04)
+    want = {"velocity": sim.stats("velocity"), "pressure": sim.stats("pressure"), "dye": dye.stats()}
+    for name in want:
+        assert got[name] == list(want[name]), f"{name}: C host {got[name]} != mirror {list(want[name])}"
