@@ -86,13 +86,16 @@ __global__ void k_dye_tables(float* __restrict__ nx, float* __restrict__ ny, con
     if (i < dg.hl) ny[i] = ((float)(i + dg.y0) / (float)dg.hg) * (float)vh;
 }
 
+// A thread's 4 cells are 32 columns apart (x0, x0 + 32, x0 + 64, x0 + 96): the 32 lanes of a warp then gather
+// from neighbouring addresses, 8-9 sectors per request instead of ~27 with 4 consecutive cells per thread
+// (that layout kept the L1 wavefront pipe 91 % busy - the kernel's limiter, profiles/r1c_cfg3_k_dye_advect*).
 template <bool SLAB>
 __global__ void __launch_bounds__(D4X * D4Y)
 k_dye_advect4(const float* __restrict__ din, float* __restrict__ dout, const Geom dg, const float2* __restrict__ vel,
               const uint8_t* __restrict__ obs, const Geom vg, const float* __restrict__ nxt,
               const float* __restrict__ nyt, float rx, float ry, float dt, float speed, float diss,
               int* __restrict__ err) {
-    const int x0 = (blockIdx.x * D4X + threadIdx.x) * 4;
+    const int x0 = blockIdx.x * (D4X * 4) + threadIdx.x;
     const int y = blockIdx.y * D4Y + threadIdx.y;
     if (x0 >= dg.w || y >= dg.hl) return;
     const int pw = dg.w, ph = dg.hg, vw = vg.w, vh = vg.hg;
@@ -104,18 +107,18 @@ k_dye_advect4(const float* __restrict__ din, float* __restrict__ dout, const Geo
     const float2* vrow_t = vel + lin(vg, 0, held_row<SLAB>(vg, vty, err));
     const float2* vrow_b = vel + lin(vg, 0, held_row<SLAB>(vg, vby, err));
     const uint8_t* orow = obs + lin(vg, 0, held_row<SLAB>(vg, (int)(unsigned)ny, err));
-    const float4 nx4 = *reinterpret_cast<const float4*>(nxt + x0);       // pw % 4 == 0
-    const float nxs[4] = {nx4.x, nx4.y, nx4.z, nx4.w};
-    float out[4];
+    float* drow = dout + lin(dg, 0, y);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float nx = nxs[j];
+        const int x = x0 + 32 * j;
+        if (x >= pw) break;
+        const float nx = nxt[x];
         const int vtx = (int)clampf(ceilf(nx), 0.0f, mx), vbx = (int)clampf(floorf(nx), 0.0f, mx);
         const float vdx = nx - (float)vbx;
         const float2 lt = vrow_t[vbx], rt = vrow_t[vtx], lb = vrow_b[vbx], rb = vrow_b[vtx];
         const float vx = mixf(mixf(lb.x, rb.x, vdx), mixf(lt.x, rt.x, vdx), vdy) * rx;
         const float vy = mixf(mixf(lb.y, rb.y, vdx), mixf(lt.y, rt.y, vdx), vdy) * ry;
-        const float fx = (float)(x0 + j) - vx * dt * speed;
+        const float fx = (float)x - vx * dt * speed;
         const float fy = (float)gy - vy * dt * speed;
         const Corners q = corners(fx, fy, pw, ph);
         const float* drow_t = din + lin(dg, 0, held_row<SLAB>(dg, q.ty, err));
@@ -123,9 +126,8 @@ k_dye_advect4(const float* __restrict__ din, float* __restrict__ dout, const Geo
         const float g1 = mixf(drow_t[q.bx], drow_t[q.tx], q.dx);
         const float g2 = mixf(drow_b[q.bx], drow_b[q.tx], q.dx);
         const float r = mixf(g2, g1, q.dy) * diss;
-        out[j] = orow[(unsigned)nx] != OBS_FREE ? 0.0f : r;
+        __stcs(drow + x, orow[(unsigned)nx] != OBS_FREE ? 0.0f : r);
     }
-    stg_stream(reinterpret_cast<float4*>(dout + lin(dg, x0, y)), make_float4(out[0], out[1], out[2], out[3]));
 }
 
 // ref: demo/shaders/demo.ComputeShader.comp:9-21 - the dye value replicated into the four channels of

@@ -67,18 +67,50 @@ __device__ __forceinline__ float2 advect_gather(const float2* __restrict__ vin, 
     return o;
 }
 
+// The same back-trace in two halves, so that the four gathers of a cell can be in flight across a whole row
+// of arithmetic (PIPE variant of k_preproject): issue = corners, addresses, loads; finish = the three mixes.
+struct Gather { float2 lt, rt, lb, rb; float dx, dy; };
+template <bool SLAB>
+__device__ __forceinline__ void gather_issue(Gather& q, const float2* __restrict__ vin, const Geom& g, int x, int gy,
+                                             float2 vel, float dt, float speed, int* __restrict__ err) {
+    const float fx = (float)x - vel.x * dt * speed;
+    const float fy = (float)gy - vel.y * dt * speed;
+    Corners c = corners(fx, fy, g.w, g.hg);
+    if (SLAB) {
+        const int lo = g.y0 - g.halo, hi = g.y0 + g.hl + g.halo - 1;
+        if (c.by < lo || c.ty > hi) *err = 1;
+        c.by = clampi(c.by, lo, hi);
+        c.ty = clampi(c.ty, lo, hi);
+    }
+    const float2* rb_ = vin + (ptrdiff_t)(c.by - g.y0) * g.w;
+    const float2* rt_ = rb_ + (c.ty - c.by) * g.w;
+    q.lt = rt_[c.bx]; q.rt = rt_[c.tx]; q.lb = rb_[c.bx]; q.rb = rb_[c.tx];
+    q.dx = c.dx; q.dy = c.dy;
+}
+__device__ __forceinline__ float2 gather_finish(const Gather& q, float diss) {
+    const float h1x = mixf(q.lt.x, q.rt.x, q.dx), h1y = mixf(q.lt.y, q.rt.y, q.dx);
+    const float h2x = mixf(q.lb.x, q.rb.x, q.dx), h2y = mixf(q.lb.y, q.rb.y, q.dx);
+    float2 o;
+    o.x = clampf(mixf(h2x, h1x, q.dy) * diss, -1.0f, 1.0f);
+    o.y = clampf(mixf(h2y, h1y, q.dy) * diss, -1.0f, 1.0f);
+    return o;
+}
+
 // InitBoundaries (shader.InitBoundaries.comp:14-34) is NOT folded in here: when has_borders is set the
 // border lines of the READ buffer are zeroed in place by k_zero_borders first, exactly like the
 // reference's dispatch does (2 (W + H) cells; cheaper than testing every gathered corner).
-template <bool VISCOUS, bool SLAB>
-__global__ void __launch_bounds__(PWARPS * 32, 2)
+// PIPE = false: 8 warps x 2 CTAs per SM, the gathers of a row are consumed in the same iteration.
+// PIPE = true : 12 warps x 1 CTA per SM (168 registers); the gathers of row ly+1 are issued before the
+//               vorticity / confinement / divergence arithmetic of row ly and consumed one iteration later.
+template <bool VISCOUS, bool SLAB, bool PIPE>
+__global__ void __launch_bounds__(PIPE ? 384 : 256, PIPE ? 1 : 2)
 k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, float2* __restrict__ vout,
              float* __restrict__ vort, float* __restrict__ div, uint8_t* __restrict__ nbmask, const Geom g,
              const PreParams prm, int* __restrict__ err) {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int DEPTH = VISCOUS ? 4 : 3;            // rows between the advected row and the divergence row
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * PWARPS + warp;
+    const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
     if (tile >= prm.ntiles) return;
     const int chunk = tile / prm.nstrips, strip = tile - chunk * prm.nstrips;
     const int x0 = strip * (PSW - 2 * PHX) - PHX;
@@ -115,25 +147,52 @@ k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, fl
     };
     fetch_row(out_lo - DEPTH);
 
+    // PIPE: gathers in flight for the row about to be advected
+    Gather G[4];
+    uint32_t g_ow = 0u;
+    bool g_valid = false;
+    auto issue_row = [&](int ly_) {          // consumes the fetched centre cells of row ly_, fetches row ly_+1
+        const int gy_ = g.y0 + ly_;
+        const uint32_t ow = ow_n;
+        const float4 c01 = c01_n, c23 = c23_n;
+        fetch_row(ly_ + 1);
+        g_valid = gy_ >= 0 && gy_ < g.hg && ly_ < out_hi + DEPTH;
+        if (g_valid) {
+            const float2 cv[4] = {make_float2(c01.x, c01.y), make_float2(c01.z, c01.w), make_float2(c23.x, c23.y),
+                                  make_float2(c23.z, c23.w)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gather_issue<SLAB>(G[j], vin, g, xc0 + j, gy_, cv[j], prm.dt, prm.speed, err);
+            g_ow = ow;
+        }
+    };
+    if (PIPE) issue_row(out_lo - DEPTH);
+
     for (int ly = out_lo - DEPTH; ly < out_hi + DEPTH; ++ly) {
         const int gy = g.y0 + ly;
         // ---- stage 0: advect row ly (ref: shader.AdvectVelocity.comp:27-50).  All 4 cells are traced
         // without branching (16 independent gathers in flight); solid cells are zeroed afterwards.
         float2 An[4];
-        const uint32_t ow = ow_n;
-        const float4 c01 = c01_n, c23 = c23_n;
-        fetch_row(ly + 1);
-        if (gy >= 0 && gy < g.hg) {
-            const float2 cv[4] = {make_float2(c01.x, c01.y), make_float2(c01.z, c01.w), make_float2(c23.x, c23.y),
-                                  make_float2(c23.z, c23.w)};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) An[j] = advect_gather<SLAB>(vin, g, xc0 + j, gy, cv[j], prm.dt, prm.speed, prm.diss, err);
+        if (PIPE) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if ((ow >> (8 * j)) & 0xffu) An[j] = make_float2(0.0f, 0.0f);
+                An[j] = (g_valid && !((g_ow >> (8 * j)) & 0xffu)) ? gather_finish(G[j], prm.diss) : make_float2(0.0f, 0.0f);
+            issue_row(ly + 1);
         } else {
+            const uint32_t ow = ow_n;
+            const float4 c01 = c01_n, c23 = c23_n;
+            fetch_row(ly + 1);
+            if (gy >= 0 && gy < g.hg) {
+                const float2 cv[4] = {make_float2(c01.x, c01.y), make_float2(c01.z, c01.w), make_float2(c23.x, c23.y),
+                                      make_float2(c23.z, c23.w)};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) An[j] = make_float2(0.0f, 0.0f);
+                for (int j = 0; j < 4; ++j) An[j] = advect_gather<SLAB>(vin, g, xc0 + j, gy, cv[j], prm.dt, prm.speed, prm.diss, err);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if ((ow >> (8 * j)) & 0xffu) An[j] = make_float2(0.0f, 0.0f);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) An[j] = make_float2(0.0f, 0.0f);
+            }
         }
 
         // ---- stage 1: vorticity of row r1 = ly-1 (ref: shader.CalcVorticity.comp:20-26)
@@ -508,22 +567,26 @@ int launch_preproject(const float2* vin, const uint8_t* obs, float2* vout, float
     prm.dt = dt; prm.speed = speed; prm.diss = diss; prm.scale = scale; prm.alpha = alpha; prm.rbeta = rbeta;
     prm.nstrips = (g.w + (PSW - 2 * PHX) - 1) / (PSW - 2 * PHX);
     const int rows = r1 - r0;
-    int nchunks = (sm_count * PWARPS * 2) / prm.nstrips;        // one tile per resident warp
+    static const bool pipe = [] { const char* e = getenv("NATRIX_PRE_PIPE"); return e ? atoi(e) != 0 : true; }();
+    const int warps = pipe ? 12 : PWARPS, resident = pipe ? 1 : 2;
+    int nchunks = (sm_count * warps * resident) / prm.nstrips;  // one tile per resident warp
     if (nchunks < 1) nchunks = 1;
     int ch = (rows + nchunks - 1) / nchunks;
     if (ch < 16) ch = 16;
     prm.ch = ch;
     nchunks = (rows + ch - 1) / ch;
     prm.ntiles = prm.nstrips * nchunks;
-    const int blocks = (prm.ntiles + PWARPS - 1) / PWARPS;
+    const int blocks = (prm.ntiles + warps - 1) / warps;
     const bool slab = g.hl != g.hg;
-    if (viscous) {
-        if (slab) k_preproject<true, true><<<blocks, PWARPS * 32, 0, st>>>(vin, obs, vout, vort, div, nbmask, g, prm, err);
-        else k_preproject<true, false><<<blocks, PWARPS * 32, 0, st>>>(vin, obs, vout, vort, div, nbmask, g, prm, err);
+#define NATRIX_PRE(V, S, P) k_preproject<V, S, P><<<blocks, warps * 32, 0, st>>>(vin, obs, vout, vort, div, nbmask, g, prm, err)
+    if (pipe) {
+        if (viscous) { if (slab) NATRIX_PRE(true, true, true); else NATRIX_PRE(true, false, true); }
+        else { if (slab) NATRIX_PRE(false, true, true); else NATRIX_PRE(false, false, true); }
     } else {
-        if (slab) k_preproject<false, true><<<blocks, PWARPS * 32, 0, st>>>(vin, obs, vout, vort, div, nbmask, g, prm, err);
-        else k_preproject<false, false><<<blocks, PWARPS * 32, 0, st>>>(vin, obs, vout, vort, div, nbmask, g, prm, err);
+        if (viscous) { if (slab) NATRIX_PRE(true, true, false); else NATRIX_PRE(true, false, false); }
+        else { if (slab) NATRIX_PRE(false, true, false); else NATRIX_PRE(false, false, false); }
     }
+#undef NATRIX_PRE
     return 1;
 }
 
