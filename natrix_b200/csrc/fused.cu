@@ -567,12 +567,16 @@ int launch_preproject(const float2* vin, const uint8_t* obs, float2* vout, float
     prm.dt = dt; prm.speed = speed; prm.diss = diss; prm.scale = scale; prm.alpha = alpha; prm.rbeta = rbeta;
     prm.nstrips = (g.w + (PSW - 2 * PHX) - 1) / (PSW - 2 * PHX);
     const int rows = r1 - r0;
-    static const bool pipe = [] { const char* e = getenv("NATRIX_PRE_PIPE"); return e ? atoi(e) != 0 : true; }();
+    // PIPE pays off once the grid fills the GPU; small grids are latency-bound per warp and prefer the variant
+    // with more, lighter CTAs (measured: 640x360 and 1024^2 vs 4096^2 and 32768x4096)
+    static const int pipe_env = [] { const char* e = getenv("NATRIX_PRE_PIPE"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+    const bool pipe = pipe_env >= 0 ? pipe_env != 0 : (size_t)g.w * (size_t)(r1 - r0) >= ((size_t)4 << 20);
     const int warps = pipe ? 12 : PWARPS, resident = pipe ? 1 : 2;
     int nchunks = (sm_count * warps * resident) / prm.nstrips;  // one tile per resident warp
     if (nchunks < 1) nchunks = 1;
     int ch = (rows + nchunks - 1) / nchunks;
-    if (ch < 16) ch = 16;
+    static const int min_ch = [] { const char* e = getenv("NATRIX_PRE_MINCH"); return e && atoi(e) > 0 ? atoi(e) : 4; }();
+    if (ch < min_ch) ch = min_ch;
     prm.ch = ch;
     nchunks = (rows + ch - 1) / ch;
     prm.ntiles = prm.nstrips * nchunks;
