@@ -186,6 +186,13 @@ int natrix_comm_stream(natrix_sim* sim, void** stream);
 int natrix_get_timings(natrix_sim* sim, float* ms, int n);
 /* Number of kernels (and memsets) this handle has launched since creation. */
 int natrix_launch_count(natrix_sim* sim, unsigned long long* kernels);
+/* Host-only introspection (no CUDA call, works without a device): the tile plan of the temporally blocked
+ * Jacobi kernel for `depth` sweeps over rows [row0, row1) of a `width`-column grid, given the obstacle hints
+ * of a step - nboxes x (x0, x1, y0, y1) half-open boxes, or circles encoded as (cx, -1 - radius, cy, 0).
+ * Writes up to `cap` tiles as (strip, first row, end row, 0); a strip is 120 (depth <= 4) or 112 output
+ * columns wide.  Returns the number of tiles.  Results of a step never depend on the plan. */
+int natrix_debug_plan_tiles(int width, int depth, int row0, int row1, const int* boxes, int nboxes,
+                            int max_tiles, int* out4, int cap);
 const char* natrix_last_error(void);
 const char* natrix_version(void);
 

@@ -1103,6 +1103,14 @@ int natrix_get_timings(natrix_sim* s, float* ms, int n) {
     return 0;
 }
 
+int natrix_debug_plan_tiles(int width, int depth, int row0, int row1, const int* boxes, int nboxes, int max_tiles,
+                            int* out4, int cap) {
+    NEED(width >= 256 && width % 16 == 0, "the temporally blocked kernel needs width % 16 == 0 and width >= 256");
+    NEED(depth >= 1 && depth <= JACOBI_TB_MAX_DEPTH && row1 > row0 && max_tiles > 0, "bad plan arguments");
+    NEED((nboxes == 0 || boxes) && nboxes >= 0 && (cap == 0 || out4) && cap >= 0, "null argument");
+    return jacobi_tb_plan_debug(width, depth, row0, row1, boxes, nboxes, max_tiles, out4, cap);
+}
+
 int natrix_launch_count(natrix_sim* s, unsigned long long* kernels) {
     NEED(s && kernels, "null argument");
     *kernels = s->launches;

@@ -676,6 +676,16 @@ void jacobi_tb_destroy(JacobiTB* tb) {
 }
 const char* jacobi_tb_error(JacobiTB* tb) { return tb ? tb->err.c_str() : "null JacobiTB"; }
 
+int jacobi_tb_plan_debug(int w, int depth, int r0, int r1, const int* boxes, int nboxes, int max_tiles, int* out4,
+                         int cap) {
+    const int hx = depth <= 4 ? 4 : 8;
+    const std::vector<int4> tiles = JacobiTB::cut_tiles(w, r0, r1, hx, depth, boxes, nboxes, max_tiles, 2.3, 0);
+    for (size_t i = 0; i < tiles.size() && (int)i < cap; ++i) {
+        out4[4 * i] = tiles[i].x; out4[4 * i + 1] = tiles[i].y; out4[4 * i + 2] = tiles[i].z; out4[4 * i + 3] = tiles[i].w;
+    }
+    return (int)tiles.size();
+}
+
 bool jacobi_tb_supported(const Geom& g) {
     // TMA needs 16-byte row pitches for the float fields and the byte mask
     return g.w % 16 == 0 && g.w >= SW;

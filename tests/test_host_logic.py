@@ -121,3 +121,56 @@ def test_checkpoint_round_trip_continues_bit_identically(tmp_path):
     _, c, cd = make()
     with pytest.raises(ValueError):
         checkpoint.load(tmp_path / "c.npz", c, [])              # dye count mismatch
+
+
+def _plan(width, depth, r0, r1, boxes, max_tiles):
+    import ctypes as C
+
+    from natrix_b200 import _lib as L
+
+    flat = (C.c_int * max(1, 4 * len(boxes)))(*[int(v) for b in boxes for v in b])
+    cap = 4 * max_tiles + 64
+    out = (C.c_int * (4 * cap))()
+    n = L.check(L.lib().natrix_debug_plan_tiles(width, depth, r0, r1, flat, len(boxes), max_tiles, out, cap))
+    assert n <= cap
+    return np.array(out[:4 * n], dtype=np.int64).reshape(n, 4)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_jacobi_tile_plan_partitions_every_strip(seed):
+    """The obstacle-aware tile planner of the temporally blocked Jacobi kernel (host code, no device needed):
+    whatever the obstacle hints, every strip's tiles cover the row range exactly once."""
+    rng = np.random.default_rng(seed)
+    width = int(rng.choice([256, 1024, 4096, 32768]))
+    depth = int(rng.integers(1, 9))
+    r0 = int(rng.integers(-24, 1))
+    r1 = r0 + int(rng.choice([9, 64, 360, 4096 + 48]))
+    boxes = []
+    for _ in range(int(rng.integers(0, 40))):
+        if rng.uniform() < 0.6:                                  # a circle: (cx, -1 - r, cy, 0)
+            boxes.append((rng.integers(0, width), -1 - int(rng.integers(1, 600)), rng.integers(r0 - 50, r1 + 50), 0))
+        else:
+            x0, y0 = int(rng.integers(0, width)), int(rng.integers(r0 - 20, r1))
+            boxes.append((x0, x0 + int(rng.integers(1, 900)), y0, y0 + int(rng.integers(1, 700))))
+    max_tiles = int(rng.choice([148 * 12, 148 * 16, 200]))
+    tiles = _plan(width, depth, r0, r1, boxes, max_tiles)
+    pitch = 128 - 2 * (4 if depth <= 4 else 8)
+    nstrips = -(-width // pitch)
+    assert len(tiles) >= nstrips and set(tiles[:, 0]) == set(range(nstrips)) and (tiles[:, 3] == 0).all()
+    for st in range(nstrips):
+        t = tiles[tiles[:, 0] == st]
+        t = t[np.argsort(t[:, 1])]
+        assert t[0, 1] == r0 and t[-1, 2] == r1, f"strip {st} does not span the rows"
+        assert (t[1:, 1] == t[:-1, 2]).all() and (t[:, 2] > t[:, 1]).all(), f"strip {st} has a gap or an overlap"
+    assert np.array_equal(tiles, _plan(width, depth, r0, r1, boxes, max_tiles))      # deterministic
+    if len(boxes) == 0 and (r1 - r0) * nstrips >= 8 * max_tiles:
+        assert len(tiles) <= max_tiles + nstrips                                       # about one tile per warp
+
+
+def test_jacobi_tile_plan_is_shorter_where_obstacles_are():
+    free = _plan(4096, 8, 0, 4096, [], 148 * 12)
+    circ = _plan(4096, 8, 0, 4096, [(2048, -1 - 700, 2048, 0)], 148 * 12)
+    h = lambda t, st: (t[t[:, 0] == st][:, 2] - t[t[:, 0] == st][:, 1])
+    mid, edge = 2048 // 112, 0
+    assert h(circ, mid).min() < h(free, mid).min()             # the strip through the circle is cut finer ...
+    assert h(circ, edge).mean() >= h(free, edge).mean()        # ... and the free strips get the longer tiles
