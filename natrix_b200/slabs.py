@@ -416,14 +416,14 @@ def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
         line = {
             "metric": metric, "value": value, "unit": metric, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong" if "strong" in w.name else "weak",
+            "scaling": "weak" if "weak" in w.name else "strong",       # only config 5 grows with N
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w.name, "grid": [w.width, w.height], "per_gpu_grid": [w.width, slab.rows],
                        "jacobi_iterations": w.iterations, "obstacles_per_step": len(w.circles),
                        "dye_grid": list(w.dye_size) if w.dye_size else None,
                        "parallelism": f"row-slabs x{world}, halo {slab.halo} rows, NCCL send/recv"
                                       + (", pressure exchanges overlapped with interior Jacobi" if slab.overlap else ""),
-                       "jacobi_depth": depth, "l2": "per-GPU state 4.6 GB exceeds L2; no flush needed",
+                       "jacobi_depth": depth, "l2": f"per-GPU state {34 * w.width * slab.rows / 1e9:.1f} GB exceeds the 126 MB L2; no flush needed",
                        "algorithmic_GBps_per_gpu": algo / world / (ms_per_step * 1e-3) / 1e9},
             "weak_base": {"workload": w1.name, "n_gpus": 1, "value": base_value, "ms_per_step": float(bms.item()),
                           "note": "same per-GPU slab run standalone on every rank of this box (max over ranks)"},
