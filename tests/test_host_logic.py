@@ -174,3 +174,27 @@ def test_jacobi_tile_plan_is_shorter_where_obstacles_are():
     mid, edge = 2048 // 112, 0
     assert h(circ, mid).min() < h(free, mid).min()             # the strip through the circle is cut finer ...
     assert h(circ, edge).mean() >= h(free, edge).mean()        # ... and the free strips get the longer tiles
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU port timed on the host cores) needs no GPU: one JSON line with the
+    keys the measurement contract names."""
+    import json
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", "demo",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "Mcell-steps/s" == d["unit"] and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["config"]["workload"] == "demo-640x360" and d["dtype"] == "f32" and d["data"] == "synthetic"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "demo-640x360" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
