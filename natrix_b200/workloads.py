@@ -193,3 +193,65 @@ def fields_of(sim, dye=None) -> dict:
     if dye is not None:
         out["dye"] = np.array(dye.particles)
     return out
+
+
+def random_scenario(seed: int, max_size: int = 160):
+    """A seeded script of public-API calls (sizes, parameters, obstacles, impulses, dye splats, per-frame dt)
+    for differential tests: ``play_scenario`` replays it on any engine (CUDA product, NumPy oracle, C oracle)."""
+    rng = np.random.default_rng(1000 + seed)
+    w = int(rng.choice([int(rng.integers(1, max_size)), 16 * int(rng.integers(16, max(17, max_size // 8 + 17)))]))
+    h = int(rng.integers(1, max_size))
+    scn = {
+        "size": (w, h), "dye_size": (int(rng.integers(1, 2 * max_size)), int(rng.integers(1, 2 * max_size))),
+        "iterations": int(rng.integers(1, 30)), "speed": float(rng.choice([1.0, 120.0, 500.0, 1000.0])),
+        "dissipation": float(rng.choice([1.0, 0.97, 0.5])), "vorticity": float(rng.choice([0.0, 1.0, 7.5])),
+        "viscosity": float(rng.choice([0.0, 0.1, 3.0])), "has_borders": bool(rng.integers(0, 2)),
+        "dye_dissipation": float(rng.choice([1.0, 0.98])), "v0_scale": float(rng.choice([0.3, 1.0, 1.7])),
+        "v0_seed": int(rng.integers(0, 2**31)), "frames": [],
+    }
+    for k in range(int(rng.integers(2, 5))):
+        frame = {"dt": 0.0 if (k == 0 and rng.uniform() < 0.3) else float(np.float32(rng.choice([1 / 60, 1 / 30, 0.004]))),
+                 "circles": [], "triangles": [], "splats": [], "dye": []}
+        for _ in range(int(rng.integers(0, 4))):
+            frame["circles"].append((float(rng.uniform(-0.1, 1.1)), float(rng.uniform(-0.1, 1.1)),
+                                     float(rng.choice([0.0, 1.5, rng.uniform(1, 0.4 * max(w, h) + 2)])), bool(rng.integers(0, 2))))
+        for _ in range(int(rng.integers(0, 2))):
+            frame["triangles"].append(tuple(float(v) for v in rng.uniform(-0.1, 1.1, 6)) + (bool(rng.integers(0, 2)),))
+        for _ in range(int(rng.integers(0, 4))):
+            frame["splats"].append((float(rng.uniform(0, 1)), float(rng.uniform(0, 1)), float(rng.uniform(-3, 3)),
+                                    float(rng.uniform(-3, 3)), float(rng.uniform(0.5, 0.3 * max(w, h) + 1))))
+        for _ in range(int(rng.integers(0, 3))):
+            frame["dye"].append((float(rng.uniform(0, 1)), float(rng.uniform(0, 1)), float(rng.uniform(1, max_size / 2)),
+                                 float(rng.uniform(0.01, 400.0))))
+        scn["frames"].append(frame)
+    return scn
+
+
+def play_scenario(scn, sim_cls: Callable, dye_cls: Optional[Callable], on_frame: Optional[Callable] = None):
+    """Replay a ``random_scenario`` through the reference's public API (demo call order); returns (sim, dye)."""
+    w, h = scn["size"]
+    sim = sim_cls(w, h, None)
+    for p in ("iterations", "speed", "dissipation", "vorticity", "viscosity", "has_borders"):
+        setattr(sim, p, scn[p])
+    rng = np.random.default_rng(scn["v0_seed"])
+    set_velocity(sim, (scn["v0_scale"] * rng.uniform(-1.0, 1.0, (h, w, 2))).astype(np.float32))
+    dye = None
+    if dye_cls is not None:
+        dye = dye_cls(scn["dye_size"][0], scn["dye_size"][1], sim, None)
+        dye.dissipation, dye.speed = scn["dye_dissipation"], scn["speed"]
+    for k, f in enumerate(scn["frames"]):
+        for (px, py, r, static) in f["circles"]:
+            sim.add_circle_obstacle((px, py), r, static)
+        for (*p, static) in f["triangles"]:
+            sim.add_triangle_obstacle((p[0], p[1]), (p[2], p[3]), (p[4], p[5]), static)
+        sim.update(f["dt"])
+        if dye is not None:
+            dye.update(f["dt"])
+        for (px, py, vx, vy, r) in f["splats"]:
+            sim.add_velocity((px, py), (vx, vy), r)
+        if dye is not None:
+            for (px, py, r, s) in f["dye"]:
+                dye.add_particles((px, py), r, s)
+        if on_frame is not None:
+            on_frame(k, sim, dye)
+    return sim, dye

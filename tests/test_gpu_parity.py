@@ -470,3 +470,20 @@ def test_pure_c_host_matches_the_python_mirror():
     want = {"velocity": sim.stats("velocity"), "pressure": sim.stats("pressure"), "dye": dye.stats()}
     for name in want:
         assert got[name] == list(want[name]), f"{name}: C host {got[name]} != mirror {list(want[name])}"
+
+
+@pytest.mark.parametrize("pipeline", [0, 1])
+@pytest.mark.parametrize("seed", range(20))
+def test_random_scenarios_vs_c_oracle(seed, pipeline):
+    """Differential test on seeded random scripts of public-API calls (workloads.random_scenario): ragged and
+    1-cell-wide grids, every parameter corner, obstacles partly outside the grid, zero radii, dt = 0, dye grids of
+    unrelated size - every field of every frame bit-identical to the C oracle."""
+    scn = W.random_scenario(seed)
+    frames = {}
+    W.play_scenario(scn, COracleFluidSimulator, COracleSmoothParticlesArea,
+                    lambda k, s, d: frames.__setitem__(k, {n: a.copy() for n, a in W.fields_of(s, d).items()}))
+
+    def check(k, s, d):
+        assert_fields_close(W.fields_of(s, d), frames[k], f"seed {seed} {scn['size']} frame {k}: ", exact=True)
+
+    W.play_scenario(scn, _sim_cls(pipeline), SmoothParticlesArea, check)
