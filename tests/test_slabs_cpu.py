@@ -300,3 +300,118 @@ def test_velocity_rows_for_dye():
     assert velocity_rows_for_dye(4096, 4096, 8) == 0          # same grid: a dye row samples exactly its own velocity row
     assert velocity_rows_for_dye(720, 360, 2) == 1            # the demo's 2x dye grid: one row below (ceil of x.5)
     assert 1 <= velocity_rows_for_dye(1000, 360, 3) <= 2
+
+
+# ------------------------------------------------------------------------------------------ the whole step
+FW, FH, FHALO, FDEPTH, FITER, FSTEPS, FSPEED = 40, 66, 10, 2, 13, 3, 120.0
+
+
+class NumpyFullStepRig:
+    """Every phase of SlabSimulator.update on an OracleFluidSimulator over the GLOBAL grid whose arrays only carry
+    data in the rows this rank holds (own rows + exchanged halos); everything else is poison (1e6 velocity,
+    NaN pressure / divergence), so a missing or too-short exchange ruins the rows that are compared."""
+
+    supports_overlap = False
+
+    def __init__(self, rank, world, v0):
+        self.r0, self.rn = partition_rows(FH, world)[rank]
+        s = self.sim = O.OracleFluidSimulator(FW, FH, None)
+        s.speed, s.vorticity, s.viscosity, s.iterations = FSPEED, 1.5, 0.4, FITER
+        v = np.full((FH, FW, 2), 1e6, np.float32)
+        v[self.r0:self.r0 + self.rn] = v0[self.r0:self.r0 + self.rn]
+        s.velocity = v
+
+    def _poison(self, a, value):
+        a[:self.r0] = value
+        a[self.r0 + self.rn:] = value
+
+    def rows_needed(self, phase, dt):
+        return {0: int(np.ceil(1.25 * dt * FSPEED)) + 5, 1: 0, 2: FDEPTH, 3: 1}[phase]
+
+    def stream_context(self, comm=False):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def halo_region(self, field, side, rows):
+        s = self.sim
+        a = {"velocity": s.velocity, "pressure": s.pressure, "divergence": s.divergence, "nbmask": None}[field]
+        if a is None:
+            t = torch.zeros(rows * FW, dtype=torch.uint8)
+            return t, t.clone()
+        if side == 0:
+            send, recv = a[self.r0:self.r0 + rows], a[self.r0 - rows:self.r0]
+        else:
+            end = self.r0 + self.rn
+            send, recv = a[end - rows:end], a[end:end + rows]
+        return torch.from_numpy(send), torch.from_numpy(recv)
+
+    def phase(self, phase, dt, sweeps=0):
+        s = self.sim
+        with np.errstate(invalid="ignore", over="ignore"):
+            if phase == 0:                                     # fluid_simulator.py:181-228
+                if s.has_borders:
+                    O.init_boundaries(s._vel[s.VELOCITY_READ])
+                s._vel[s.VELOCITY_WRITE] = O.advect_velocity(s.velocity, s.obstacles, np.float32(dt), s.speed, s.dissipation)
+                s._flip_v()
+                s.vorticity_field = O.calc_vorticity(s.velocity)
+                s._vel[s.VELOCITY_WRITE] = O.apply_vorticity(s.velocity, s.vorticity_field, np.float32(dt), s.vorticity)
+                s._flip_v()
+                alpha, rbeta = O.viscosity_alpha_rbeta(s.viscosity)
+                s._vel[s.VELOCITY_WRITE] = O.viscosity_sweep(s.velocity, alpha, rbeta)
+                s._flip_v()
+            elif phase == 1:                                   # :231-248
+                s.divergence = O.divergence(s.velocity, s.obstacles)
+                self._poison(s.divergence, np.nan)
+                s._p[s.PRESSURE_READ] = np.zeros_like(s._p[0])
+            elif phase == 2:                                   # :251-255
+                for _ in range(sweeps):
+                    s._p[s.PRESSURE_WRITE] = O.poisson_sweep(s.pressure, s.divergence, s.obstacles)
+                    s._flip_p()
+            elif phase == 3:                                   # :258-280
+                s._vel[s.VELOCITY_WRITE] = O.subtract_gradient(s.velocity, s.pressure, s.obstacles)
+                s._flip_v()
+                s.obstacles = np.zeros_like(s.obstacles)
+                self._poison(s._vel[s.VELOCITY_READ], 1e6)
+                self._poison(s._p[s.PRESSURE_READ], np.nan)
+
+    def own(self, a):
+        return a[self.r0:self.r0 + self.rn]
+
+
+def _full_step_script(sim, k):
+    sim.add_circle_obstacle((0.45, 0.5), 6.0)                   # straddles the slab boundaries
+    sim.add_triangle_obstacle((0.1, 0.1), (0.5, 0.2), (0.2, 0.45))
+    sim.update(1.0 / 60.0)
+    sim.add_velocity((0.5, 0.34 + 0.15 * k), (0.8, -0.6), 7.0)
+
+
+def _full_step_worker(rank, world, port, errors):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        v0 = np.random.default_rng(21).uniform(-0.9, 0.9, (FH, FW, 2)).astype(np.float32)
+        ref = O.OracleFluidSimulator(FW, FH, None)
+        ref.speed, ref.vorticity, ref.viscosity, ref.iterations = FSPEED, 1.5, 0.4, FITER
+        ref.velocity = v0
+        rig = NumpyFullStepRig(rank, world, v0)
+        slab = SlabSimulator(FW, FH, engine=rig, halo=FHALO, depth=FDEPTH)
+        slab.iterations = FITER
+        for k in range(FSTEPS):
+            _full_step_script(ref, k)
+            _full_step_script(slab, k)
+            for name in ("velocity", "pressure", "divergence"):
+                a, b = rig.own(getattr(rig.sim, name)), rig.own(getattr(ref, name))
+                assert a.tobytes() == b.tobytes(), f"step {k}: {name} differs in {int((a != b).sum())} values"
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001 - reported to the parent
+        import traceback
+        errors.put(f"rank {rank}: {e}\n{traceback.format_exc()}")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_whole_step_over_slabs_matches_single_process_oracle_over_gloo(world):
+    """advect -> vorticity -> confinement -> viscosity -> divergence -> Jacobi -> gradient with the exchange
+    schedule of SlabSimulator.update, three frames with obstacles and impulses across the slab boundaries; a
+    velocity halo of 2 rows instead of ceil(1.25 dt speed) + 5 makes it fail."""
+    _run_world(_full_step_worker, world)
