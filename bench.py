@@ -7,8 +7,10 @@ A "step" is one frame of the reference's demo loop over one synthetic workload (
 FluidSimulator.update -> dye update -> velocity/dye impulses):
 
 * every N: config 5 of BASELINE.json - weak scaling, one 32768 x 4096 row slab per GPU (global grid
-  32768 x 4096 N), 200 Jacobi iterations per step, 64 circular obstacles per step; N > 1 runs under
-  torchrun, one rank per GPU, halo exchange over NCCL.  The per-N values therefore form ONE series.
+  32768 x 4096 N), 200 Jacobi iterations per step, 64 circular obstacles per step AND per GPU (the
+  1-GPU domain tiled N times along y, so cells and obstacle load per GPU are fixed); N > 1 runs under
+  torchrun, one rank per GPU, halo exchange over NCCL overlapped with the interior Jacobi launches.
+  The per-N values therefore form ONE series.
 * the N = 1 line also carries `config3_4096`: config 3 - 4096^2 velocity + 4096^2 dye, 100 iterations,
   8 velocity + 8 dye splats and one circular obstacle per step (`--workload cfg3` makes it the primary).
 
