@@ -51,6 +51,25 @@ def assert_fields_close(got: dict, want: dict, what: str = "", exact: bool = Fal
             assert ndiff == 0, f"{what}{name}: {ndiff} elements are not bit-identical (max err {err:.3e})"
 
 
+def parity_oracle():
+    """(sim, dye, sim_mt, dye_mt, kind): the oracle classes the GPU parity tests compare against.  oracle/_ref (the
+    reference's own shader text, compiled) when its library is present; else the restated oracles."""
+    from oracle import natrix_ref as R
+
+    if R.available():
+        return (R.RefFluidSimulator, R.RefSmoothParticlesArea, R.RefFluidSimulator, R.RefSmoothParticlesArea,
+                "reference shader text compiled as C++ (oracle/_ref/libnatrix_ref.so)")
+    from oracle.c_oracle import COracleFluidSimulator, COracleSmoothParticlesArea
+    from oracle.natrix_oracle import OracleFluidSimulator, OracleSmoothParticlesArea
+
+    return (OracleFluidSimulator, OracleSmoothParticlesArea, COracleFluidSimulator, COracleSmoothParticlesArea,
+            "restated oracles (oracle/natrix_oracle.py, oracle/natrix_oracle.c) - oracle/_ref missing")
+
+
+def pytest_report_header(config):
+    return f"natrix parity oracle: {parity_oracle()[4]}"
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return ROOT / "tests" / "golden"

@@ -1,17 +1,24 @@
-"""Regenerates the golden fixtures in this directory FROM THE NUMPY ORACLE.
+"""Regenerates the golden fixtures in this directory FROM THE REFERENCE ITSELF.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py          (needs /root/reference: run in the build container)
 
-The reference itself cannot produce vectors (its bgfx engine does not run here and it ships
-no fixtures: "parity unpinned", see oracle/natrix_oracle.py), so these files pin the oracle
-against accidental change, and give the GPU tests a fixed answer that does not depend on the
-oracle code being importable.
+The vectors are produced by the reference's UNMODIFIED Python classes (natrix/core/fluid_simulator.py,
+demo/smooth_particles_area.py, imported from /root/reference) driving the reference's UNMODIFIED shader
+text compiled as C++ (oracle/_ref, see oracle/ref_shim/bgfx_compute.sh for the few definitions the shader
+dialect leaves to bgfx).  Only the bgfx engine is replaced.  PROVENANCE.json records the SHA-256 of every
+reference file that took part.  The reference cannot travel to the GPU box, these files do; they pin the
+restated oracles (oracle/natrix_oracle.py, oracle/natrix_oracle.c), the restated dispatch driver
+(oracle/natrix_ref.py) and the CUDA product to the same bits.
 
 * small_case.npz     - every field after each of 4 steps of a 96x64 grid (dye 192x128) with a
                        circle, a static triangle, splats, vorticity and viscosity;
 * digests.json       - SHA-256 of the raw float32 bytes of every field for the BASELINE.json
                        configurations that fit a CPU test (config 1 after 1 and 3 steps, a
-                       256x256 cut of config 2 after 2 steps).
+                       256x256 cut of config 2 after 2 steps);
+* scenario_digests.json - SHA-256 of every field after every frame of the 24 seeded random API scripts of
+                       natrix_b200.workloads.random_scenario (landscape or square dye grids only match the
+                       reference literally - SURVEY Q12 - so portrait dye grids are splatted over the full
+                       grid by all engines and the reference Python is not used for those seeds' dye).
 """
 from __future__ import annotations
 
@@ -75,8 +82,56 @@ def run_digests(sim_cls, dye_cls):
     return res
 
 
+def dye_splat_is_literal(scn) -> bool:
+    """True when the reference's (groups_x, groups_x) splat dispatch (smooth_particles_area.py:80-82)
+    covers the whole dye grid, i.e. the literal reference and the intended full-grid splat coincide."""
+    pw, ph = scn["dye_size"]
+    return -(-pw // 16) >= -(-ph // 16)
+
+
+def scenario_digests(engine_for, seeds=range(24)):
+    """`engine_for(scn)` -> (sim_cls, dye_cls)."""
+    res = {}
+    for seed in seeds:
+        scn = W.random_scenario(seed)
+        frames = {}
+        sim_cls, dye_cls = engine_for(scn)
+        W.play_scenario(scn, sim_cls, dye_cls,
+                        lambda k, s, d: frames.__setitem__(f"frame{k}", {n: digest(a) for n, a in W.fields_of(s, d).items()}))
+        res[f"seed{seed}"] = frames
+    return res
+
+
+def provenance():
+    from oracle import natrix_ref as R
+
+    files = sorted((R.REFERENCE_ROOT / "natrix" / "core" / "shaders" / "originals").glob("*")) + [
+        R.REFERENCE_ROOT / "demo" / "shaders" / "shader.AddParticle.comp",
+        R.REFERENCE_ROOT / "demo" / "shaders" / "shader.AdvectParticle.comp",
+        R.REFERENCE_ROOT / "natrix" / "core" / "fluid_simulator.py",
+        R.REFERENCE_ROOT / "natrix" / "core" / "common" / "constants.py",
+        R.REFERENCE_ROOT / "natrix" / "core" / "utils" / "shaders_utils.py",
+        R.REFERENCE_ROOT / "demo" / "smooth_particles_area.py"]
+    return {"generator": "tests/golden/make_golden.py",
+            "engine": "unmodified reference Python classes over oracle/_ref/libnatrix_ref.so (reference shader text compiled by g++)",
+            "shim_build": R.lib("literal").nref_build_info().decode(),
+            "reference_files_sha256": {str(f.relative_to(R.REFERENCE_ROOT)): hashlib.sha256(f.read_bytes()).hexdigest()
+                                       for f in files if f.is_file()}}
+
+
 if __name__ == "__main__":
-    np.savez_compressed(HERE / "small_case.npz", **small_case(OracleFluidSimulator, OracleSmoothParticlesArea))
-    (HERE / "digests.json").write_text(json.dumps(run_digests(OracleFluidSimulator, OracleSmoothParticlesArea),
-                                                  indent=1, sort_keys=True) + "\n")
+    from oracle import natrix_ref as R
+
+    RefSim, RefDye, _ = R.reference_classes("literal")
+
+    def engine_for(scn):
+        # portrait dye grids: the reference's own splat dispatch misses rows (Q12, treated as a bug by every engine
+        # here), so those seeds run the restated dispatch driver over the same compiled shaders instead
+        return (RefSim, RefDye) if dye_splat_is_literal(scn) else (R.RefFluidSimulator, R.RefSmoothParticlesArea)
+
+    np.savez_compressed(HERE / "small_case.npz", **small_case(RefSim, RefDye))
+    (HERE / "digests.json").write_text(json.dumps(run_digests(RefSim, RefDye), indent=1, sort_keys=True) + "\n")
+    (HERE / "scenario_digests.json").write_text(
+        json.dumps(scenario_digests(engine_for), indent=1, sort_keys=True) + "\n")
+    (HERE / "PROVENANCE.json").write_text(json.dumps(provenance(), indent=1, sort_keys=True) + "\n")
     print("wrote", HERE / "small_case.npz", (HERE / "small_case.npz").stat().st_size, "bytes")

@@ -13,10 +13,24 @@ from natrix_b200 import _lib as L
 from natrix_b200 import workloads as W
 from natrix_b200.core.fluid_simulator import FluidSimulator
 from natrix_b200.smooth_particles_area import SmoothParticlesArea
-from oracle.c_oracle import COracleFluidSimulator, COracleSmoothParticlesArea
-from oracle.natrix_oracle import OracleFluidSimulator, OracleSmoothParticlesArea
+from conftest import parity_oracle
+
+# The oracle of every test below is oracle/_ref - the reference's own shader text compiled as C++ and driven in
+# the reference's dispatch order (oracle/natrix_ref.py) - whenever its prebuilt library is present (it is built
+# where /root/reference exists and travels to the GPU box); the restated C / NumPy oracles, proven bit-identical
+# to it by tests/test_ref_oracle.py, are the fallback.  The names keep saying which restatement a test used to
+# take; `ORACLE_KIND` says what is actually in use (also printed in the pytest header).
+(OracleFluidSimulator, OracleSmoothParticlesArea, COracleFluidSimulator, COracleSmoothParticlesArea,
+ ORACLE_KIND) = parity_oracle()
 
 pytestmark = pytest.mark.gpu
+
+
+def test_the_parity_oracle_is_the_reference_shader_text():
+    if not ORACLE_KIND.startswith("reference"):
+        pytest.skip(f"oracle/_ref not present here; parity checked against: {ORACLE_KIND}")
+    from oracle import natrix_ref as R
+    assert b"source=" in R.lib("literal").nref_build_info()
 
 
 def _mg():
