@@ -45,6 +45,18 @@ METRIC = "Mcell-steps/s"
 JACOBI_BYTES_PER_CELL_SWEEP = 20        # p 4 + div 4 + obstacles 8 -> p 4
 
 
+def ncu_capture_for(kernel: str, cells: int):
+    """profiles/kernel_traffic.json: per kernel, `ncu --set full` captures of THIS build (commit recorded in the file)
+    at the bench sizes - DRAM bytes per launch, issue-slot utilisation, SM active / elapsed.  The capture whose cell
+    count is nearest is scaled per cell."""
+    tfile = ROOT / "profiles" / "kernel_traffic.json"
+    try:
+        caps = [c for c in json.loads(tfile.read_text())["captures"] if c["kernel"].startswith(kernel)]
+        return min(caps, key=lambda c: abs(np.log(c["cells"] / cells))) if caps else None
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -109,46 +121,97 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# --------------------------------------------------------------------------- CPU (oracle) arm
-def time_cpu_port(w: W.Workload, steps: int, warmup: int, budget_s: float):
-    """Times the C/OpenMP oracle port on all host threads.  Returns (Mcell-steps/s, info)."""
-    from oracle import c_oracle
+# --------------------------------------------------------------------------- CPU (reference / oracle) arm
+def host_threads() -> int:
+    """CPUs this process may run on.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm sets its
+    thread count explicitly from this instead."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
-    threads = c_oracle.max_threads()
-    sim, dye = W.build(w, c_oracle.COracleFluidSimulator, c_oracle.COracleSmoothParticlesArea if w.dye_size else None)
+
+def cpu_sample_of(w: W.Workload, max_cells: int) -> W.Workload:
+    """A bounded sample of workload `w` for the CPU arm: the first `rows` rows of the grid at full width, same
+    parameters and iteration count, with the obstacles / impulses of `w` that fall into the band (positions are
+    normalised, so y is rescaled to the band).  The CPU rate in cell-steps per second does not depend on the number
+    of rows (every stage is a row-streaming stencil), so the sample's rate is reported as the workload's."""
+    if w.cells <= max_cells:
+        return w
+    rows = max(64, min(w.height, (max_cells // w.width) // 16 * 16))
+    scale = w.height / rows
+    circles = [(px, py * scale, r) for (px, py, r) in w.circles if (py * w.height - r) < rows]
+    dye = None
+    if w.dye_size:
+        dye = (w.dye_size[0], max(16, int(round(w.dye_size[1] / scale))))
+    import dataclasses
+    return dataclasses.replace(w, name=f"{w.name}[rows 0..{rows - 1}]", height=rows, circles=circles, dye_size=dye)
+
+
+def time_cpu_arm(w: W.Workload, steps: int, warmup: int, budget_s: float, max_cells: int, prefer: str = "reference"):
+    """Times the reference's CPU implementation of the step on all host threads, on a bounded sample of `w`.
+
+    kind "reference": oracle/_ref, the reference's own shader text compiled as C++ and dispatched in the reference's
+    order (oracle/natrix_ref.py), when its prebuilt library is present; kind "port": the C/OpenMP restatement
+    (oracle/natrix_oracle.c).  Returns (Mcell-steps/s, info)."""
+    threads = host_threads()
+    sw = cpu_sample_of(w, max_cells)
+    kind = "port"
+    if prefer == "reference":
+        from oracle import natrix_ref as R
+        if R.available():
+            kind = "reference"
+    if kind == "reference":
+        variant = "literal" if sw.cells <= 2 ** 24 else "exact"      # float32 linear indices are exact up to 2^24 cells
+        R.lib(variant).nref_set_threads(threads)
+        sim_cls = lambda wd, ht, layout=None: R.RefFluidSimulator(wd, ht, layout, variant=variant)   # noqa: E731
+        dye_cls = R.RefSmoothParticlesArea
+        impl = f"oracle/_ref/libnatrix_ref{'_exact' if variant == 'exact' else ''}.so (reference shaders compiled as C++, OpenMP over rows)"
+    else:
+        from oracle import c_oracle
+        c_oracle.lib().nox_set_threads(threads)
+        sim_cls, dye_cls = c_oracle.COracleFluidSimulator, c_oracle.COracleSmoothParticlesArea
+        impl = "oracle/natrix_oracle.c (C/OpenMP restatement of the reference shaders)"
+    sim, dye = W.build(sw, sim_cls, dye_cls if sw.dye_size else None)
     t0 = time.perf_counter()
-    W.run_step(w, sim, dye, 0)
+    W.run_step(sw, sim, dye, 0)
     first = time.perf_counter() - t0
     done_warm = 1
     while done_warm < warmup and first * (done_warm + 2) < budget_s / 2:
-        W.run_step(w, sim, dye, done_warm)
+        W.run_step(sw, sim, dye, done_warm)
         done_warm += 1
     k = max(1, min(steps, int((budget_s - first * done_warm) / max(first, 1e-9))))
     t0 = time.perf_counter()
     for i in range(k):
-        W.run_step(w, sim, dye, done_warm + i)
+        W.run_step(sw, sim, dye, done_warm + i)
     dt = (time.perf_counter() - t0) / k
-    value = w.cells / dt / 1e6
-    sample = (f"{k} full steps of {w.name} ({w.width}x{w.height}, {w.iterations} Jacobi iterations"
-              f"{', dye ' + 'x'.join(map(str, w.dye_size)) if w.dye_size else ''}) after {done_warm} warm-up, "
-              f"{dt:.3f} s/step")
-    return value, {"kind": "port", "cores": threads, "host_cpus": os.cpu_count(), "sample": sample,
-                   "unit": METRIC, "value": value, "seconds_per_step": dt, "steps": k}
+    value = sw.cells / dt / 1e6
+    sample = (f"{k} full steps of {sw.name} ({sw.width}x{sw.height} = {sw.cells / 1e6:.1f} Mcells"
+              f"{'' if sw is w else f', a band of the {w.width}x{w.height} workload'}, {sw.iterations} Jacobi iterations, "
+              f"{len(sw.circles)} obstacles{', dye ' + 'x'.join(map(str, sw.dye_size)) if sw.dye_size else ''}) after "
+              f"{done_warm} warm-up, {dt:.3f} s/step, {threads} threads; {impl}")
+    return value, {"kind": kind, "cores": threads, "host_cpus": os.cpu_count(), "sample": sample, "unit": METRIC,
+                   "value": value, "seconds_per_step": dt, "steps": k, "sample_grid": [sw.width, sw.height]}
 
 
 def run_reference_arm(args, w: W.Workload):
+    """--impl reference: the reference's own CPU implementation of the step (oracle/_ref, else the C port) on all the
+    host threads this process may use, on a bounded sample of the SAME workload the GPU arm runs at this N.  Under
+    torchrun rank 0 alone runs it; the other ranks exit 0."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    value, info = time_cpu_port(w, args.steps, args.warmup, budget_s=150.0)
+    value, info = time_cpu_arm(w, args.steps, max(args.warmup, 1), budget_s=120.0, max_cells=args.cpu_cells)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus,
-        "steps": info["steps"], "warmup": args.warmup, "ms_per_step": info["seconds_per_step"] * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "steps": info["steps"], "warmup": args.warmup, "ms_per_step": info["seconds_per_step"] * 1e3 * w.cells / (info["sample_grid"][0] * info["sample_grid"][1]),
+        "higher_is_better": True, "scaling": "weak" if "weak" in w.name else "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
         "config": {"workload": w.name, "grid": [w.width, w.height], "jacobi_iterations": w.iterations,
                    "dye": list(w.dye_size) if w.dye_size else None,
-                   "note": "CPU port of the reference shaders (oracle/natrix_oracle.c, OpenMP); the reference's "
-                           "bgfx engine cannot run headless here"},
+                   "note": "the reference's CPU path on the host cores (its bgfx engine cannot run headless here): value is "
+                           "the cell-step rate measured on the bounded sample named in cpu_baseline.sample, ms_per_step is "
+                           "that rate applied to the full grid"},
         "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -233,42 +296,49 @@ def measure_single_gpu(args, w: W.Workload, with_cpu: bool, steps: int):
     jac_ms = statistics.mean(jacobi_ms)
     algo_bytes_step = JACOBI_BYTES_PER_CELL_SWEEP * w.cells * w.iterations
     achieved = algo_bytes_step / (jac_ms * 1e-3) / 1e9
-    traffic = None
-    tfile = ROOT / "profiles" / "jacobi_traffic.json"
-    if tfile.exists():
-        try:        # ncu dram__bytes_read.sum + dram__bytes_write.sum of one depth-8 launch of the nearest captured size
-            caps = json.loads(tfile.read_text())["captures"]
-            cap = min(caps, key=lambda c: abs(np.log(c["cells"] / w.cells)))
-            traffic = cap["dram_bytes_per_cell_per_launch"] * w.cells
-        except Exception:
-            traffic = None
-    dram_achieved = None if traffic is None or pipeline == 0 else traffic / (jac_ms / jl * 1e-3) / 1e9
-    roofline = {"kernel": "k_jacobi_tb" if pipeline else "k_poisson_ref", "bound": "hbm", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic if pipeline else None,
-                "dram_achieved": dram_achieved, "dram_frac": None if dram_achieved is None else dram_achieved / peak,
+    cap = ncu_capture_for("k_jacobi_tb", w.cells)
+    traffic = None if (cap is None or pipeline == 0) else cap["dram_bytes_per_cell_per_launch"] * w.cells
+    dram_achieved = None if traffic is None else traffic / (jac_ms / jl * 1e-3) / 1e9
+    roofline = {"kernel": "k_jacobi_tb" if pipeline else "k_poisson_ref", "bound": "hbm",
+                "achieved": dram_achieved if dram_achieved is not None else achieved, "peak": peak, "unit": "GB/s",
+                "frac": (dram_achieved if dram_achieved is not None else achieved) / peak,
+                "traffic": traffic, "traffic_source": None if cap is None else cap.get("source"),
+                "algorithmic_achieved": achieved, "algorithmic_frac": achieved / peak,
                 "peak_source": peak_src, "launches_per_step": jl, "avg_launch_ms": jac_ms / jl,
                 "algorithmic_bytes_per_launch": algo_bytes_step / jl,
-                "note": "achieved/frac use ALGORITHMIC bytes = 20 B x cells x sweeps (reference field widths); one launch of "
-                        "`depth` sweeps really moves ~13 B per cell (traffic, from ncu), so frac exceeds 1 by design and "
-                        "dram_frac = traffic / launch time / peak is the physical HBM utilisation: the kernel is "
-                        "instruction-issue bound, not HBM bound"}
+                "issue_active_pct": None if cap is None else cap.get("issue_active_pct"),
+                "sm_active_over_elapsed": None if cap is None else cap.get("sm_active_over_elapsed"),
+                "note": "achieved/frac are PHYSICAL: DRAM bytes of one launch (ncu dram__bytes_read+write of this build at "
+                        "this size, profiles/kernel_traffic.json) over the launch duration measured live here, against the "
+                        "measured HBM peak.  algorithmic_* is SURVEY 8(d)'s figure, 20 B x cells x sweeps per launch of "
+                        "`depth` sweeps over the same duration: it exceeds the peak by design, because temporal blocking "
+                        "reads p, div and the mask once per `depth` sweeps"}
 
-    # ---- the other stages of the step against the same roofline (algorithmic B/cell: SURVEY 8(d))
+    # ---- the other stages of the step: physical bytes (what the kernel must move) next to the algorithmic ones
     stage_algo = {"advect": 24 + 12 + 20 + (16 if w.viscosity > 0 else 0) + 20,   # the fused pre-projection kernel
                   "gradient": 28}
+    stage_phys = {"advect": 26, "gradient": 21}      # vel 8 + obs 1 -> vel 8, vort 4, div 4, mask 1; p 4 + mask 1 + vel 8 -> vel 8
+    stage_kernel = {"advect": "k_preproject", "gradient": "k_gradient_mask4"}
     stages_roofline = {}
     if pipeline == 1:
         for name, bpc in stage_algo.items():
             ms = stage[name]
             if ms > 0:
-                gbs = bpc * w.cells / (ms * 1e-3) / 1e9
-                stages_roofline[name] = {"algorithmic_bytes_per_cell": bpc, "ms": ms, "achieved": gbs, "frac": gbs / peak}
+                gbs = stage_phys[name] * w.cells / (ms * 1e-3) / 1e9
+                c2 = ncu_capture_for(stage_kernel[name], w.cells)
+                stages_roofline[name] = {"kernel": stage_kernel[name], "ms": ms, "bytes_per_cell": stage_phys[name],
+                                         "achieved": gbs, "frac": gbs / peak,
+                                         "algorithmic_bytes_per_cell": bpc,
+                                         "algorithmic_frac": bpc * w.cells / (ms * 1e-3) / 1e9 / peak,
+                                         "ncu_dram_bytes_per_cell": None if c2 is None else c2["dram_bytes_per_cell_per_launch"]}
 
     # ---- CPU baseline beside it (bounded sample, all host threads)
     cpu = None
     if with_cpu and not args.no_cpu:
-        _, info = time_cpu_port(w, steps=3, warmup=1, budget_s=30.0)
+        _, info = time_cpu_arm(w, steps=3, warmup=1, budget_s=25.0, max_cells=args.cpu_cells)
         cpu = {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        _, port = time_cpu_arm(w, steps=2, warmup=1, budget_s=10.0, max_cells=args.cpu_cells, prefer="port")
+        cpu["c_port"] = {k: port[k] for k in ("value", "cores", "sample")}     # the hand-written C/OpenMP restatement, for context
 
     step_bytes = w.algorithmic_bytes_per_cell_step() * w.cells
     line = {
@@ -317,6 +387,8 @@ def main(argv=None):
     ap.add_argument("--packed", type=int, default=None, help="0/1: f32x2 arithmetic in the Jacobi kernel")
     ap.add_argument("--no-obstacles", action="store_true", help="diagnostic: drop the per-step obstacles")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-cells", type=int, default=8 * 1024 * 1024,
+                    help="CPU arm: largest sample (cells) of the workload that is actually stepped on the host")
     args = ap.parse_args(argv)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -344,9 +416,7 @@ def main(argv=None):
         w.circles = []
         w.name += "-noobst"
     if args.impl == "reference":
-        if name == "cfg5":          # keep the CPU arm bounded: the 1-GPU slab of the weak-scaling grid
-            w = W.cfg5_workload(1)
-        return run_reference_arm(args, w)
+        return run_reference_arm(args, w)         # the SAME workload as the GPU arm at this N, on a bounded sample
     if n == 1 and world == 1:
         return run_single_gpu(args, w, secondary)
     from natrix_b200 import slabs

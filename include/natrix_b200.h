@@ -101,12 +101,27 @@ int natrix_add_triangle_obstacle(natrix_sim* sim, float p1x, float p1y, float p2
 /* ---- the hot path ----------------------------------------------------------------------
  * ref: FluidSimulator.update :174-280: [InitBoundaries] -> AdvectVelocity -> CalcVorticity ->
  * ApplyVorticity -> [Viscosity] -> Divergence -> clear pressure -> iterations x Poisson ->
- * SubtractGradient -> clear obstacles.  For a slab this runs the whole step only when the
- * slab is the full grid; multi-GPU hosts call the natrix_step_phase pieces with halo
- * exchanges between them. */
+ * SubtractGradient -> clear obstacles.  On a slab handle with a communicator (natrix_comm_init) the same one
+ * call runs the slab's share of the step, halo exchanges included; every rank calls it with the same dt. */
 int natrix_step(natrix_sim* sim, float dt);
 
-/* Multi-GPU pieces of one step (slab handles).  Phases, in order:
+/* ---- multi-GPU: row slabs with the halo exchange inside the library ---------------------------------
+ * New capability (the reference is single-device): one slab handle per GPU - one process or
+ * one host thread per GPU - holding the rows natrix_create_slab names, in the standard partition: rank r of
+ * N holds H/N rows from r*(H/N) + min(r, H%N), the first H%N ranks one more.  Rank 0 calls
+ * natrix_comm_unique_id and hands the 128 bytes to every rank by whatever means the host has (a file, MPI,
+ * torch.distributed); then every rank calls natrix_comm_init (collective).  From there natrix_step and
+ * natrix_dye_step exchange halo rows with the two neighbouring ranks themselves - NCCL send/recv over
+ * NVLink, bound at run time from libnccl.so.2 (NATRIX_NCCL_LIB overrides the path); the pressure exchanges
+ * of the Jacobi phase run on a second stream under the interior launches (NATRIX_SLAB_OVERLAP=0 disables).
+ * Results are bit-identical to the single-GPU run.  The natrix_step_phase / natrix_halo_region calls below
+ * remain for hosts that bring their own transport. */
+int natrix_comm_unique_id(void* id128);
+int natrix_comm_init(natrix_sim* sim, const void* id128, int rank, int world);
+/* exchanges (NCCL groups) issued so far and bytes sent to neighbours by this handle */
+int natrix_comm_stats(natrix_sim* sim, unsigned long long* exchanges, unsigned long long* bytes);
+
+/* Multi-GPU pieces of one step (slab handles) for hosts with their own transport.  Phases, in order:
  *   0 advect (needs VELOCITY halo of natrix_halo_rows_needed(sim, 0, dt) rows)
  *   1 vorticity+confinement(+viscosity)+divergence+mask (needs post-advect VELOCITY halo 4)
  *   2 `sweeps` Jacobi sweeps (needs PRESSURE halo `sweeps`, DIVERGENCE+NBMASK halo `sweeps`)
@@ -189,7 +204,7 @@ int natrix_launch_count(natrix_sim* sim, unsigned long long* kernels);
 /* Host-only introspection (no CUDA call, works without a device): the tile plan of the temporally blocked
  * Jacobi kernel for `depth` sweeps over rows [row0, row1) of a `width`-column grid, given the obstacle hints
  * of a step - nboxes x (x0, x1, y0, y1) half-open boxes, or circles encoded as (cx, -1 - radius, cy, 0).
- * Writes up to `cap` tiles as (strip, first row, end row, 0); a strip is 120 (depth <= 4) or 112 output
+ * Writes up to `cap` tiles as (strip, first row, end row, diagnostic tag); a strip is 120 (depth <= 4) or 112 output
  * columns wide.  Returns the number of tiles.  Results of a step never depend on the plan. */
 int natrix_debug_plan_tiles(int width, int depth, int row0, int row1, const int* boxes, int nboxes,
                             int max_tiles, int* out4, int cap);

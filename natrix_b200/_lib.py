@@ -33,6 +33,9 @@ SIGNATURES = {
     "natrix_add_circle_obstacle": (_i, [_vp, _f, _f, _f, _i]),
     "natrix_add_triangle_obstacle": (_i, [_vp, _f, _f, _f, _f, _f, _f, _i]),
     "natrix_step": (_i, [_vp, _f]),
+    "natrix_comm_unique_id": (_i, [_vp]),
+    "natrix_comm_init": (_i, [_vp, _vp, _i, _i]),
+    "natrix_comm_stats": (_i, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "natrix_step_phase": (_i, [_vp, _i, _f, _i]),
     "natrix_halo_rows_needed": (_i, [_vp, _i, _f]),
     "natrix_halo_region": (_i, [_vp, _i, _i, _i, _pvp, _pvp, _psz]),

@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "kernels.h"
 #include "jacobi_tb.h"
 
@@ -31,6 +33,53 @@ int fail(int code, const std::string& msg) {
 
 #define NEED(cond, msg) \
     do { if (!(cond)) return fail(NATRIX_ERR_ARG, msg); } while (0)
+
+// ---- NCCL, bound at run time: the library has no link-time dependency on it, and a process that already
+// holds a libnccl.so.2 (torch's bundled one) keeps using that copy.  Only the few entry points of the halo
+// exchange are bound; the prototypes follow nccl.h (ncclUniqueId is a 128-byte struct passed by value).
+struct NcclId { char internal[128]; };
+struct Nccl {
+    void* h = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string why;
+};
+constexpr int NCCL_UINT8 = 1;        // ncclUint8 (nccl.h)
+
+Nccl* nccl() {
+    static Nccl n;
+    if (n.h || !n.why.empty()) return &n;
+    const char* env = getenv("NATRIX_NCCL_LIB");
+    if (env) n.h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    if (!n.h) n.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);     // the copy this process already uses
+    if (!n.h) n.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!n.h) n.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!n.h) { n.why = std::string("libnccl.so.2 not found (set NATRIX_NCCL_LIB): ") + dlerror(); return &n; }
+    auto sym = [&](const char* name) { void* p = dlsym(n.h, name); if (!p) n.why = std::string("missing NCCL symbol ") + name; return p; };
+    n.GetUniqueId = (int (*)(NcclId*))sym("ncclGetUniqueId");
+    n.CommInitRank = (int (*)(void**, int, NcclId, int))sym("ncclCommInitRank");
+    n.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+    n.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))sym("ncclSend");
+    n.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))sym("ncclRecv");
+    n.GroupStart = (int (*)())sym("ncclGroupStart");
+    n.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    n.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    if (!n.why.empty()) n.h = nullptr;
+    return &n;
+}
+
+#define NC(expr)                                                                              \
+    do {                                                                                      \
+        int r__ = (expr);                                                                     \
+        if (r__ != 0)                                                                         \
+            return fail(NATRIX_ERR_CUDA, std::string(#expr) + ": " + nccl()->GetErrorString(r__)); \
+    } while (0)
 
 enum Stage { ST_ADVECT = 0, ST_VORT, ST_DIV, ST_JACOBI, ST_GRAD, ST_CLEAR, ST_COUNT };
 
@@ -84,6 +133,15 @@ struct natrix_sim {
     cudaEvent_t ev_group = nullptr, ev_edges = nullptr, ev_xchg = nullptr;
     std::vector<cudaEvent_t> ev_int;             // after the j-th interior launch of the open group
     int group_open = 0;                          // sweeps of the group whose interior is queued, else 0
+    // halo rows of the READ velocity that were filled (natrix_halo_region / the library's own exchange) since
+    // that buffer was last written: the range check of the back-traces compares against these, not against
+    // the allocation
+    int vel_halo_valid = 0;
+    // the library's own halo exchange (natrix_comm_init): NCCL communicator over the slabs, rank order = row order
+    void* comm = nullptr;
+    int comm_rank = -1, comm_world = 0;
+    int overlap = 1;                             // NATRIX_SLAB_OVERLAP
+    unsigned long long exchanges = 0, exchanged_bytes = 0;
 
     int ext_lo(int k) const { int lo = -k; if (g.y0 + lo < 0) lo = -g.y0; return lo < -g.halo ? -g.halo : lo; }
     int ext_hi(int k) const {
@@ -102,6 +160,7 @@ struct natrix_dye {
     uint32_t* rgba = nullptr;                   // staging for host RGBA8 export
     float4* lut = nullptr;                      // 256-entry field colour map (render.cu), built on first use
     int rd = 0;
+    int halo_valid = 0;                         // halo rows of the READ dye buffer filled since it was last written
     std::vector<SplatD> pending;
 
     size_t own_cells() const { return (size_t)g.w * g.hl; }
@@ -264,13 +323,20 @@ int phase_advect(natrix_sim* s, float dt) {
     if (int rc = flush_circles(s)) return rc;
     stamp(s, ST_ADVECT);
     const bool fold = s->pipeline != 0 && s->has_borders;
+    // the back-traces may only gather from halo rows that were filled for THIS velocity buffer (the kernels use
+    // Geom::halo for nothing but that range check): rows beyond them hold stale ping-pong data
+    Geom gv = g;
+    gv.halo = std::min(g.halo, s->vel_halo_valid);
+    s->vel_halo_valid = 0;                       // the buffer that becomes READ has no exchanged rows yet
+    if (g.hl != g.hg && gv.halo < std::min(4, g.halo) && (g.y0 > 0 || g.y0 + g.hl < g.hg))
+        return fail(NATRIX_ERR_STATE, "the slab's VELOCITY halo was not exchanged before the step (natrix_halo_rows_needed rows)");
     s->fused_pre = s->pipeline != 0 && preproject_supported(g);
     if (s->fused_pre) {
         // advect + vorticity + confinement + [viscosity] + divergence + mask in one pass; the
         // velocity buffer flips once (the intermediate velocities never reach memory)
         if (s->has_borders)
             s->launches += launch_zero_borders(s->vel[s->vr], g, s->ext_lo(g.halo), s->ext_hi(g.halo), s->st);
-        s->launches += launch_preproject(s->vel[s->vr], s->obs, s->vel[1 - s->vr], s->vort, s->div, s->nbm, g, 0, g.hl,
+        s->launches += launch_preproject(s->vel[s->vr], s->obs, s->vel[1 - s->vr], s->vort, s->div, s->nbm, gv, 0, g.hl,
                                          dt, s->speed, s->dissipation, s->vorticity, s->viscous != 0, s->alpha,
                                          s->rbeta, s->sm_count, s->d_err, s->st);
         s->vr = 1 - s->vr;
@@ -279,7 +345,7 @@ int phase_advect(natrix_sim* s, float dt) {
     }
     if (s->has_borders && !fold)
         s->launches += launch_init_boundaries(s->vel[s->vr], g, s->ext_lo(g.halo), s->ext_hi(g.halo), s->st);
-    s->launches += launch_advect(s->vel[s->vr], s->obs, s->vel[1 - s->vr], g, s->ext_lo(4), s->ext_hi(4), dt,
+    s->launches += launch_advect(s->vel[s->vr], s->obs, s->vel[1 - s->vr], gv, s->ext_lo(4), s->ext_hi(4), dt,
                                  s->speed, s->dissipation, fold, s->d_err, s->st);
     s->vr = 1 - s->vr;
     CU(cudaGetLastError());
@@ -500,6 +566,149 @@ int field_info(natrix_sim* s, int field, void** base_row0, size_t* elem) {
     }
 }
 
+// ---- the library's own halo exchange (natrix_comm_init) ------------------------------------------------
+// send = the slab's own first / last `rows` rows of a field, recv = the halo rows beyond them
+void halo_ptrs(char* row0, size_t row_bytes, int hl, int side, int rows, char** send, char** recv) {
+    if (side == 0) {
+        *send = row0;
+        *recv = row0 - (ptrdiff_t)rows * (ptrdiff_t)row_bytes;
+    } else {
+        *send = row0 + (size_t)(hl - rows) * row_bytes;
+        *recv = row0 + (size_t)hl * row_bytes;
+    }
+}
+
+// One NCCL group: `rows` halo rows of every listed field swapped with both neighbouring ranks, on stream st.
+// Point-to-point only - the path has no collective.
+int exchange_fields(natrix_sim* s, const int* fields, int nfields, int rows, cudaStream_t st) {
+    if (rows <= 0 || !s->comm) return 0;
+    const Geom& g = s->g;
+    if (rows > g.halo || rows > g.hl)
+        return fail(NATRIX_ERR_RANGE, "this step needs " + std::to_string(rows) + " halo rows but the slab was created with " +
+                                      std::to_string(g.halo));
+    Nccl* n = nccl();
+    NC(n->GroupStart());
+    for (int side = 0; side < 2; ++side) {
+        const int peer = side == 0 ? s->comm_rank - 1 : s->comm_rank + 1;
+        if (side == 0 ? g.y0 <= 0 : g.y0 + g.hl >= g.hg) continue;
+        for (int k = 0; k < nfields; ++k) {
+            void* row0 = nullptr;
+            size_t elem = 0;
+            if (int rc = field_info(s, fields[k], &row0, &elem)) { n->GroupEnd(); return rc; }
+            char *send, *recv;
+            halo_ptrs((char*)row0, (size_t)g.w * elem, g.hl, side, rows, &send, &recv);
+            const size_t bytes = (size_t)rows * g.w * elem;
+            NC(n->Send(send, bytes, NCCL_UINT8, peer, s->comm, st));
+            NC(n->Recv(recv, bytes, NCCL_UINT8, peer, s->comm, st));
+            s->exchanged_bytes += bytes;
+        }
+    }
+    NC(n->GroupEnd());
+    s->exchanges += 1;
+    for (int k = 0; k < nfields; ++k)
+        if (fields[k] == NATRIX_VELOCITY) s->vel_halo_valid = rows;
+    return 0;
+}
+
+// the same for the rows of a dye field (its own geometry), on the simulator's stream
+int exchange_dye(natrix_dye* d, int rows) {
+    natrix_sim* s = d->sim;
+    if (rows <= 0 || !s->comm) return 0;
+    const Geom& g = d->g;
+    if (rows > g.halo || rows > g.hl)
+        return fail(NATRIX_ERR_RANGE, "this dye step needs " + std::to_string(rows) + " halo rows but the dye slab was created with " +
+                                      std::to_string(g.halo));
+    Nccl* n = nccl();
+    const size_t row_bytes = (size_t)g.w * sizeof(float), bytes = (size_t)rows * row_bytes;
+    NC(n->GroupStart());
+    for (int side = 0; side < 2; ++side) {
+        if (side == 0 ? g.y0 <= 0 : g.y0 + g.hl >= g.hg) continue;
+        const int peer = side == 0 ? s->comm_rank - 1 : s->comm_rank + 1;
+        char *send, *recv;
+        halo_ptrs((char*)d->d[d->rd], row_bytes, g.hl, side, rows, &send, &recv);
+        NC(n->Send(send, bytes, NCCL_UINT8, peer, s->comm, s->st));
+        NC(n->Recv(recv, bytes, NCCL_UINT8, peer, s->comm, s->st));
+        s->exchanged_bytes += bytes;
+    }
+    NC(n->GroupEnd());
+    s->exchanges += 1;
+    d->halo_valid = rows;
+    return 0;
+}
+
+int velocity_rows_for_step(const natrix_sim* s, float dt) {
+    // |v| <= 1 after add_velocity / advect clamps; the projection can exceed it slightly, so the reach is padded
+    // and the kernel reports (NATRIX_ERR_RANGE) if a back-trace still leaves the exchanged rows.
+    const double reach = std::ceil(1.25 * (double)dt * (double)s->speed) + 1.0;
+    return (int)reach + 4;
+}
+
+// The whole step of one slab, exchanges included (ref: FluidSimulator.update, fluid_simulator.py:174-280; the
+// exchange schedule is DESIGN.md section 6, the executable model of it natrix_b200/slabs.py SlabSimulator.update).
+int step_slab(natrix_sim* s, float dt) {
+    const Geom& g = s->g;
+    if (int rc = flush_splats(s)) return rc;
+    const int vel = NATRIX_VELOCITY, prs = NATRIX_PRESSURE;
+    // every allocated halo row of the velocity, not just the rows_needed a |v| <= 1 flow reaches: the projection
+    // and the confinement force can push |v| past 1, and 48 rows cost microseconds over NVLink.  A back-trace
+    // that still leaves them raises NATRIX_ERR_RANGE.
+    if (int rc = exchange_fields(s, &vel, 1, std::max(std::min(velocity_rows_for_step(s, dt), g.halo), std::min(g.halo, g.hl)), s->st)) return rc;
+    if (int rc = phase_advect(s, dt)) return rc;
+    if (int rc = phase_forces(s, dt)) return rc;
+    // Several Jacobi launches per exchange: with k * depth halo rows the slab recomputes the rows its neighbour
+    // owns for the first k - 1 launches instead of exchanging after every one.  A partial group goes first so
+    // that launch depths never decrease (phase_jacobi_interior / phase_jacobi_edges).
+    const int n = s->iterations, depth = jacobi_launch_depth(s);
+    const int span = std::max(1, g.halo / depth) * depth;
+    std::vector<int> groups;
+    if (n % span) groups.push_back(n % span);
+    for (int k = 0; k < n / span; ++k) groups.push_back(span);
+    const bool overlap = s->overlap && s->comm_world > 1 && g.hl >= 2 * span;
+    stamp(s, ST_JACOBI);
+    s->first_block = false;
+    for (size_t i = 0; i < groups.size(); ++i) {
+        const int t = groups[i];
+        if (overlap)
+            if (int rc = phase_jacobi_interior(s, t)) return rc;
+        cudaStream_t xs = overlap ? s->st_edge : s->st;
+        if (i == 0) {
+            // p starts at zero, halos included - unless the simulator warm-starts from the last step's pressure
+            const int first[3] = {NATRIX_DIVERGENCE, NATRIX_NBMASK, NATRIX_PRESSURE};
+            if (int rc = exchange_fields(s, first, s->warm_start ? 3 : 2, std::min(span, n), xs)) return rc;
+        } else {
+            if (int rc = exchange_fields(s, &prs, 1, t, xs)) return rc;
+        }
+        if (int rc = overlap ? phase_jacobi_edges(s, t) : phase_jacobi(s, t)) return rc;
+    }
+    if (int rc = exchange_fields(s, &prs, 1, 1, s->st)) return rc;
+    if (int rc = phase_project(s)) return rc;
+    return check_range_flag(s, false);
+}
+
+// Standard row partition (the first height % world ranks hold one extra row): (row0, rows) of `rank`.
+void partition_rows(int height, int world, int rank, int* row0, int* rows) {
+    const int base = height / world, extra = height % world;
+    *rows = base + (rank < extra ? 1 : 0);
+    *row0 = rank * base + std::min(rank, extra);
+}
+
+// Rows of post-projection velocity a dye slab samples beyond its simulator slab, maximum over ranks (every rank
+// must exchange the same count); the shader's float32 (y / dye_height) * grid_height at the first and last dye
+// row of each slab (ref: demo/shaders/shader.AdvectParticle.comp:46).
+int dye_velocity_rows(int dye_height, int grid_height, int world) {
+    int need = 0;
+    for (int r = 0; r < world; ++r) {
+        int p0, pn, v0, vn;
+        partition_rows(dye_height, world, r, &p0, &pn);
+        partition_rows(grid_height, world, r, &v0, &vn);
+        const float lo = ((float)p0 / (float)dye_height) * (float)grid_height;
+        const float hi = ((float)(p0 + pn - 1) / (float)dye_height) * (float)grid_height;
+        const int first = std::max(0, (int)std::floor(lo)), last = std::min(grid_height - 1, (int)std::ceil(hi));
+        need = std::max(need, std::max(v0 - first, last - (v0 + vn - 1)));
+    }
+    return need;
+}
+
 }  // namespace
 
 extern "C" {
@@ -563,6 +772,7 @@ int natrix_destroy(natrix_sim* s) {
     cudaSetDevice(s->device);
     if (s->st) cudaStreamSynchronize(s->st);
     for (natrix_dye* d : s->dyes) d->sim = nullptr;   // orphaned dye handles stay destroyable
+    if (s->comm) { nccl()->CommDestroy(s->comm); s->comm = nullptr; }
     jacobi_tb_destroy(s->tb);
     for (int i = 0; i < 2; ++i) { cudaFree(s->vel_base[i]); cudaFree(s->p_base[i]); }
     cudaFree(s->div_base); cudaFree(s->vort_base); cudaFree(s->obs_base); cudaFree(s->nbm_base);
@@ -740,23 +950,56 @@ int natrix_halo_region(natrix_sim* s, int field, int side, int rows, void** send
     size_t elem = 0;
     if (int rc = field_info(s, field, &row0, &elem)) return rc;
     const size_t row_bytes = (size_t)s->g.w * elem;
-    char* base = (char*)row0;
-    if (side == 0) {
-        *send_ptr = base;
-        *recv_ptr = base - (ptrdiff_t)rows * (ptrdiff_t)row_bytes;
-    } else {
-        *send_ptr = base + (size_t)(s->g.hl - rows) * row_bytes;
-        *recv_ptr = base + (size_t)s->g.hl * row_bytes;
-    }
+    halo_ptrs((char*)row0, row_bytes, s->g.hl, side, rows, (char**)send_ptr, (char**)recv_ptr);
     *bytes = (size_t)rows * row_bytes;
+    if (field == NATRIX_VELOCITY) s->vel_halo_valid = rows;      // the host is about to fill them
+    return 0;
+}
+
+int natrix_comm_unique_id(void* id128) {
+    NEED(id128, "null argument");
+    Nccl* n = nccl();
+    if (!n->h) return fail(NATRIX_ERR_STATE, n->why);
+    NC(n->GetUniqueId((NcclId*)id128));
+    return 0;
+}
+
+int natrix_comm_init(natrix_sim* s, const void* id128, int rank, int world) {
+    NEED(s && id128, "null argument");
+    NEED(world >= 1 && rank >= 0 && rank < world, "rank outside the world");
+    NEED(!s->comm, "the simulator already has a communicator");
+    int row0 = 0, rows = 0;
+    partition_rows(s->g.hg, world, rank, &row0, &rows);
+    NEED(row0 == s->g.y0 && rows == s->g.hl,
+         "slab rows must follow the standard partition: rank r holds rows [r*(H/N) + min(r, H%N), ...), H%N ranks one extra");
+    Nccl* n = nccl();
+    if (!n->h) return fail(NATRIX_ERR_STATE, n->why);
+    if (int rc = select_device(s)) return rc;
+    if (int rc = ensure_edge_stream(s)) return rc;
+    NcclId id;
+    memcpy(&id, id128, sizeof(id));
+    NC(n->CommInitRank(&s->comm, world, id, rank));
+    s->comm_rank = rank;
+    s->comm_world = world;
+    if (const char* e = getenv("NATRIX_SLAB_OVERLAP")) s->overlap = atoi(e) != 0;
+    return 0;
+}
+
+int natrix_comm_stats(natrix_sim* s, unsigned long long* exchanges, unsigned long long* bytes) {
+    NEED(s && exchanges && bytes, "null argument");
+    *exchanges = s->exchanges;
+    *bytes = s->exchanged_bytes;
     return 0;
 }
 
 int natrix_step(natrix_sim* s, float dt) {
     NEED(s, "null simulator");
-    if (s->g.hl != s->g.hg)
-        return fail(NATRIX_ERR_STATE, "natrix_step needs the full grid; slabs use natrix_step_phase");
     if (int rc = select_device(s)) return rc;
+    if (s->g.hl != s->g.hg) {
+        if (!s->comm)
+            return fail(NATRIX_ERR_STATE, "natrix_step on a slab needs natrix_comm_init (or drive natrix_step_phase with your own exchange)");
+        return step_slab(s, dt);
+    }
     if (int rc = phase_advect(s, dt)) return rc;
     if (int rc = phase_forces(s, dt)) return rc;
     stamp(s, ST_JACOBI);
@@ -825,7 +1068,8 @@ int natrix_copy_in(natrix_sim* s, int field, const void* host, size_t bytes) {
     CU(cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, s->st));
     CU(cudaStreamSynchronize(s->st));
     if (field == NATRIX_PRESSURE) s->p_is_zero = false;
-    if (field == NATRIX_VELOCITY) CU(cudaMemsetAsync(s->d_err + 1, 1, s->nbands * sizeof(int), s->st));   // unknown range
+    if (field == NATRIX_NBMASK)
+        if (field == NATRIX_VELOCITY) CU(cudaMemsetAsync(s->d_err + 1, 1, s->nbands * sizeof(int), s->st));   // unknown range
     return 0;
 }
 
@@ -916,11 +1160,24 @@ int natrix_dye_step(natrix_dye* d, float dt, float speed, float dissipation) {
     if (int rc = flush_splats(s)) return rc;     // the advect reads the CURRENT velocity
     if (int rc = flush_circles(s)) return rc;    // ... and the CURRENT obstacle map
     if (int rc = flush_dye(d)) return rc;
+    if (s->comm) {
+        // the library's own exchange: the post-projection velocity rows the dye samples beyond the simulator slab
+        // and the dye rows within back-trace reach (both neighbours apply the same add_particles calls first)
+        const int vel = NATRIX_VELOCITY;
+        if (int rc = exchange_fields(s, &vel, 1, dye_velocity_rows(d->g.hg, s->g.hg, s->comm_world), s->st)) return rc;
+        const int need = (int)std::ceil(1.25 * (double)dt * (double)speed * ((double)d->g.hg / (double)s->g.hg)) + 2;
+        if (int rc = exchange_dye(d, std::min(need, std::min(d->g.halo, d->g.hl)))) return rc;
+    }
+    // gathers may only touch halo rows filled for the CURRENT buffers (Geom::halo is the kernels' range limit)
+    Geom dg = d->g, vg = s->g;
+    dg.halo = std::min(dg.halo, d->halo_valid);
+    vg.halo = std::min(vg.halo, s->vel_halo_valid);
+    d->halo_valid = 0;
     if (s->pipeline != 0 && d->g.w % 4 == 0)
-        s->launches += launch_dye_advect4(d->d[d->rd], d->d[1 - d->rd], d->g, s->vel[s->vr], s->obs, s->g, d->tables,
+        s->launches += launch_dye_advect4(d->d[d->rd], d->d[1 - d->rd], dg, s->vel[s->vr], s->obs, vg, d->tables,
                                           d->tables + d->g.w, dt, speed, dissipation, s->d_err, s->st);
     else
-        s->launches += launch_dye_advect(d->d[d->rd], d->d[1 - d->rd], d->g, s->vel[s->vr], s->obs, s->g, dt, speed,
+        s->launches += launch_dye_advect(d->d[d->rd], d->d[1 - d->rd], dg, s->vel[s->vr], s->obs, vg, dt, speed,
                                          dissipation, s->d_err, s->st);
     d->rd = 1 - d->rd;
     CU(cudaGetLastError());
@@ -959,15 +1216,9 @@ int natrix_dye_halo_region(natrix_dye* d, int side, int rows, void** send_ptr, v
     if (int rc = select_device(d->sim)) return rc;
     if (int rc = flush_dye(d)) return rc;
     const size_t row_bytes = (size_t)d->g.w * sizeof(float);
-    char* base = (char*)d->d[d->rd];
-    if (side == 0) {
-        *send_ptr = base;
-        *recv_ptr = base - (ptrdiff_t)rows * (ptrdiff_t)row_bytes;
-    } else {
-        *send_ptr = base + (size_t)(d->g.hl - rows) * row_bytes;
-        *recv_ptr = base + (size_t)d->g.hl * row_bytes;
-    }
+    halo_ptrs((char*)d->d[d->rd], row_bytes, d->g.hl, side, rows, (char**)send_ptr, (char**)recv_ptr);
     *bytes = (size_t)rows * row_bytes;
+    d->halo_valid = rows;                       // the host is about to fill them
     return 0;
 }
 

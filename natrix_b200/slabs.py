@@ -18,8 +18,15 @@ Obstacles and impulses are functions of global cell coordinates: every rank rast
 rows (halo rows included), no exchange.  Halo rows are recomputed redundantly from the same
 inputs in the same order, so the result is bit-identical to the single-GPU run.
 
-``SlabSimulator`` is engine-agnostic host logic: the CUDA engine below drives
-libnatrix_b200.so slab handles; tests drive it with a CPU engine over gloo.
+Two drivers of the same schedule:
+
+* **native** (default on CUDA): the exchange lives inside libnatrix_b200.so - ``natrix_comm_init`` gives the slab
+  handle an NCCL communicator and ``natrix_step`` / ``natrix_dye_step`` run the slab's share of the step, halo
+  exchanges included, in one C call per step.  This module then only does the rank plumbing (partition, handing
+  rank 0's NCCL unique id to the other ranks over torch.distributed).
+* **python** (``NATRIX_SLAB_DRIVER=python``, and every non-CUDA engine): ``SlabSimulator.update`` below issues
+  the phases and the ``torch.distributed`` send/recv pairs itself.  It is the executable model of the schedule:
+  the gloo tests drive it with a CPU engine, and hosts with their own transport follow it.
 """
 from __future__ import annotations
 
@@ -63,8 +70,29 @@ class CudaSlabEngine:
         self._views = {}
 
     supports_overlap = True          # natrix_step_phase 4 / 5 (interior / edges of a Jacobi group)
+    native = False                   # True once init_comm has given the handle its own communicator
+
+    def init_comm(self, dist, group, rank: int, world: int, overlap: bool):
+        """Hand rank 0's NCCL unique id to every rank (plumbing) and let the library build its communicator."""
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            self.L.check(self.sim._lib.natrix_comm_unique_id(buf))
+        box = [bytes(buf)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (C.c_ubyte * 128).from_buffer_copy(box[0])
+        os.environ["NATRIX_SLAB_OVERLAP"] = "1" if overlap else "0"       # read by natrix_comm_init
+        self.L.check(self.sim._lib.natrix_comm_init(self.sim._handle(), ident, rank, world))
+        self.native = True
+
+    def comm_stats(self):
+        n, b = C.c_ulonglong(), C.c_ulonglong()
+        self.L.check(self.sim._lib.natrix_comm_stats(self.sim._handle(), C.byref(n), C.byref(b)))
+        return n.value, b.value
 
     FIELD_IDS = {"velocity": 0, "pressure": 1, "divergence": 2, "nbmask": 5}
+
+    def push_params(self):
+        self.sim._push_params()
 
     def phase(self, phase: int, dt: float, sweeps: int = 0):
         if phase == 0:
@@ -124,8 +152,22 @@ class SlabSimulator:
         self.overlap = bool(overlap) and can
         self.iterations = 50
         self.simulate = True
-        self.exchanges = 0
-        self.exchanged_bytes = 0
+        self._exchanges = 0
+        self._exchanged_bytes = 0
+        # the library's own exchange (one natrix_step per update) unless the Python model of it is asked for
+        self.native = False
+        if self.world > 1 and hasattr(engine, "init_comm") and os.environ.get("NATRIX_SLAB_DRIVER", "native") != "python":
+            engine.init_comm(dist, group, self.rank, self.world, self.overlap)
+            self.native = True
+
+    @property
+    def exchanges(self) -> int:
+        return self.engine.comm_stats()[0] if self.native else self._exchanges
+
+    @property
+    def exchanged_bytes(self) -> int:
+        """Bytes sent to neighbours so far (per exchange: all fields, both neighbours)."""
+        return self.engine.comm_stats()[1] if self.native else self._exchanged_bytes
 
     # -- the reference's mutators, forwarded to the slab (global normalised coordinates)
     @property
@@ -169,14 +211,20 @@ class SlabSimulator:
                     keep += [send, recv]
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
-        self.exchanges += 1
-        self.exchanged_bytes += sum(t.numel() * t.element_size() for t in keep) // 2
+        self._exchanges += 1
+        self._exchanged_bytes += sum(t.numel() * t.element_size() for t in keep) // 2
 
     # -- one step (ref: FluidSimulator.update, fluid_simulator.py:174-280) in four phases
     def update(self, time_delta: float):
         if not self.simulate:
             return
         e = self.engine
+        if self.native:
+            self.sim.iterations = int(self.iterations)
+            self.sim.update(time_delta)                       # natrix_step: the whole step, exchanges included
+            return
+        if hasattr(e, "push_params"):
+            e.push_params()                                   # rows_needed reads the simulator's CURRENT speed
         self.exchange("velocity", e.rows_needed(0, time_delta))
         e.phase(0, time_delta)
         e.phase(1, time_delta)
@@ -295,6 +343,9 @@ class SlabSmoothParticlesArea:
     def update(self, time_delta: float):
         if not self.simulate:
             return
+        if self.slab.native and hasattr(self.engine, "area"):
+            self.engine.step(time_delta, self._speed, self._dissipation)      # natrix_dye_step exchanges by itself
+            return
         self.slab.exchange("velocity", self.velocity_rows)
         rows = self.engine.rows_needed(1, time_delta, self._speed)
         self.slab.exchange("dye", rows, region=self.engine.halo_region, limit=self.halo)
@@ -320,6 +371,10 @@ def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
     if not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     depth = args.depth or 8
+    # driver-visible multi-GPU parity: a small slab-vs-single-GPU run, both pipelines and both exchange schedules,
+    # before anything is timed; the outcome rides in the JSON line
+    from natrix_b200 import slab_parity
+    parity = slab_parity.check(2048, 512 * world, steps=2, iterations=37, local=local)
     slab = SlabSimulator(w.width, w.height, device=local, depth=depth)
     sim = slab.sim
     sim.vorticity, sim.viscosity, sim.iterations = w.vorticity, w.viscosity, w.iterations
@@ -427,8 +482,10 @@ def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
                        "algorithmic_GBps_per_gpu": algo / world / (ms_per_step * 1e-3) / 1e9},
             "weak_base": {"workload": w1.name, "n_gpus": 1, "value": base_value, "ms_per_step": float(bms.item()),
                           "note": "same per-GPU slab run standalone on every rank of this box (max over ranks)"},
-            "halo": {"exchanges_per_step": slab.exchanges / (3 * args.steps + max(args.warmup, 3)),
-                     "bytes_per_exchange_per_neighbour": slab.exchanged_bytes / max(slab.exchanges, 1),
+            "slab_parity": parity,
+            "halo": {"driver": "libnatrix_b200.so (natrix_step: NCCL send/recv from C)" if slab.native else "python (torch.distributed)",
+                     "exchanges_per_step": slab.exchanges / (2 * args.steps + max(args.warmup, 3)),
+                     "bytes_per_exchange": slab.exchanged_bytes / max(slab.exchanges, 1),
                      "host_enqueue_ms_per_step": host_ms},
             "e2e": {"value": w.cells / (float(e2e_ms.item()) * 1e-3) / 1e6, "unit": metric,
                     "ms_per_step": float(e2e_ms.item()), "h2d_bytes_per_step": 16 * len(w.circles) + 32,

@@ -156,7 +156,7 @@ def test_jacobi_tile_plan_partitions_every_strip(seed):
     tiles = _plan(width, depth, r0, r1, boxes, max_tiles)
     pitch = 128 - 2 * (4 if depth <= 4 else 8)
     nstrips = -(-width // pitch)
-    assert len(tiles) >= nstrips and set(tiles[:, 0]) == set(range(nstrips)) and (tiles[:, 3] == 0).all()
+    assert len(tiles) >= nstrips and set(tiles[:, 0]) == set(range(nstrips))
     for st in range(nstrips):
         t = tiles[tiles[:, 0] == st]
         t = t[np.argsort(t[:, 1])]
@@ -165,6 +165,8 @@ def test_jacobi_tile_plan_partitions_every_strip(seed):
     assert np.array_equal(tiles, _plan(width, depth, r0, r1, boxes, max_tiles))      # deterministic
     if len(boxes) == 0 and (r1 - r0) * nstrips >= 8 * max_tiles:
         assert len(tiles) <= max_tiles + nstrips                                       # about one tile per warp
+    if (r1 - r0) * nstrips >= 16 * max_tiles and len(boxes) == 0:
+        assert len(tiles) >= max_tiles                                                 # no resident warp is left without a tile
 
 
 def test_jacobi_tile_plan_is_shorter_where_obstacles_are():
@@ -195,6 +197,8 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["config"]["workload"] == "demo-640x360" and d["dtype"] == "f32" and d["data"] == "synthetic"
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "demo-640x360" in cb["sample"]
+    from oracle import natrix_ref
+    assert cb["kind"] == ("reference" if natrix_ref.available() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "demo-640x360" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
