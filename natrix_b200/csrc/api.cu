@@ -130,8 +130,7 @@ struct natrix_sim {
     // slabs, overlapped halo exchange: the exchange and the edge zones of a Jacobi group run on st_edge
     // while the interior runs on st (phase_jacobi_interior / phase_jacobi_edges)
     cudaStream_t st_edge = nullptr;
-    cudaEvent_t ev_group = nullptr, ev_edges = nullptr, ev_xchg = nullptr;
-    std::vector<cudaEvent_t> ev_int;             // after the j-th interior launch of the open group
+    cudaEvent_t ev_group = nullptr, ev_edges = nullptr;
     int group_open = 0;                          // sweeps of the group whose interior is queued, else 0
     // halo rows of the READ velocity that were filled (natrix_halo_region / the library's own exchange) since
     // that buffer was last written: the range check of the back-traces compares against these, not against
@@ -141,6 +140,7 @@ struct natrix_sim {
     void* comm = nullptr;
     int comm_rank = -1, comm_world = 0;
     int overlap = 1;                             // NATRIX_SLAB_OVERLAP
+    int xfirst = 0, reserve_sms = 0;             // NATRIX_SLAB_XFIRST, NATRIX_SLAB_RESERVE (see step_slab)
     unsigned long long exchanges = 0, exchanged_bytes = 0;
 
     int ext_lo(int k) const { int lo = -k; if (g.y0 + lo < 0) lo = -g.y0; return lo < -g.halo ? -g.halo : lo; }
@@ -427,21 +427,24 @@ int phase_jacobi(natrix_sim* s, int sweeps) {
 }
 
 // ---- overlapped halo exchange (slabs) ----------------------------------------------------------------
-// A group of `sweeps` Jacobi sweeps between two pressure exchanges is cut by rows.  The interior - the rows
-// whose value after the group depends on no halo row - runs on the main stream, the edge zones on st_edge
-// behind the exchange the host issues there:
+// A group of `sweeps` Jacobi sweeps between two pressure exchanges.  Only its FIRST launch is cut by rows:
+// the interior - the rows whose value after that launch depends on no halo row - runs on the main stream
+// beside the exchange, the two edge zones on st_edge behind the exchange; the remaining launches of the
+// group cover all rows in one piece on the main stream, which waits for the edge zones first.
 //
-//   launch j (depth d_j, c_j = d_1 + .. + d_j):  interior [c_j, hl - c_j)        p[src] -> p[1 - src]
-//                                                 edges    [ext_lo(sweeps - c_j), c_j) and the mirror image
+//   launch 1 (depth d_1):  interior I_1 = [d_1, hl - d_1)                          p[src] -> p[1 - src]
+//                          edges    B_1 = [ext_lo(sweeps - d_1), d_1) and the mirror image
+//   launch j > 1:          F_j = [ext_lo(sweeps - c_j), ext_hi(sweeps - c_j)),  c_j = d_1 + .. + d_j
 //
-//   main    | I_1 ............ | wait X | I_2 ...... | I_3 ...... |           | wait E | next group
-//   st_edge | exchange X | B_1 |          wait I_1 | B_2 | wait I_2 | B_3 | E
+//   main    | I_1 ....................... | wait E | F_2 ........ | F_3 ........ |  next group
+//   st_edge | wait G | exchange X | B_1 | E
 //
-// I_1 overlaps the exchange.  I_2 writes the buffer the exchange sends from, so it waits for X; from there
-// on the edge launch j only needs the interior launch j - 1 (its rows [c_{j-1}, c_j + d_j) come from there).
-// Launch depths never decrease inside a group (a partial launch goes first), so edge launch j, which reads
-// rows below c_j + d_j of its source, and interior launch j + 1, which writes rows from c_{j+1} of the same
-// buffer, never touch the same row.  The next group's interior waits for this group's edges (E).
+// I_1 reads own rows of p[src] only and writes rows of p[1 - src] that B_1 does not; X writes halo rows of
+// p[src] (and of the divergence and the mask in the first group of a step) that I_1 never reads.  F_2 writes
+// p[src], the buffer X sends from and B_1 reads: it is ordered behind both through E.  (An earlier schedule
+// cut every launch of the group: the edge blocks of launch j then shared the SMs with interior launch
+// j + 1 - one wave of blocks that each own a whole SM - and delayed it by their own duration every time;
+// measured at 2 GPUs, 32768 x 4096 per GPU: 0.58 ms of a 11.9 ms step.)
 std::vector<int> group_depths(int sweeps, int depth) {
     std::vector<int> d;
     if (sweeps % depth) d.push_back(sweeps % depth);
@@ -453,24 +456,14 @@ int ensure_edge_stream(natrix_sim* s) {
     if (s->st_edge) return 0;
     int lo = 0, hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    // highest priority: edge blocks are few and the next exchange waits for them
+    // highest priority: the exchange and the edge blocks are few and the rest of the group waits for them
     CU(cudaStreamCreateWithPriority(&s->st_edge, cudaStreamNonBlocking, hi));
     CU(cudaEventCreateWithFlags(&s->ev_group, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s->ev_edges, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&s->ev_xchg, cudaEventDisableTiming));
     return 0;
 }
 
-int interior_launch(natrix_sim* s, const std::vector<int>& depths, size_t j, int src, int done) {
-    const Geom& g = s->g;
-    const bool up = g.y0 > 0, down = g.y0 + g.hl < g.hg;
-    if (int rc = jacobi_rows(s, src, depths[j], up ? done : 0, down ? g.hl - done : g.hl, s->p_is_zero && j == 0, s->st))
-        return rc;
-    CU(cudaEventRecord(s->ev_int[j], s->st));
-    return 0;
-}
-
-// phase 4: the first interior launch of the group; the host queues the exchange on st_edge next
+// phase 4: the interior of the group's first launch; the host queues the exchange on st_edge next
 int phase_jacobi_interior(natrix_sim* s, int sweeps) {
     const Geom& g = s->g;
     const bool up = g.y0 > 0, down = g.y0 + g.hl < g.hg;
@@ -481,41 +474,32 @@ int phase_jacobi_interior(natrix_sim* s, int sweeps) {
     // everything queued so far (divergence, the previous group) precedes the exchange and the edge zones
     CU(cudaEventRecord(s->ev_group, s->st));
     CU(cudaStreamWaitEvent(s->st_edge, s->ev_group, 0));
-    const std::vector<int> depths = group_depths(sweeps, jacobi_launch_depth(s));
-    while (s->ev_int.size() < depths.size()) {
-        cudaEvent_t e = nullptr;
-        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        s->ev_int.push_back(e);
-    }
-    if (int rc = interior_launch(s, depths, 0, s->pr, depths[0])) return rc;
+    const int d1 = group_depths(sweeps, jacobi_launch_depth(s))[0];
+    if (int rc = jacobi_rows(s, s->pr, d1, up ? d1 : 0, down ? g.hl - d1 : g.hl, s->p_is_zero, s->st)) return rc;
     s->group_open = sweeps;
     CU(cudaGetLastError());
     return 0;
 }
 
-// phase 5: the exchange is queued on st_edge; edge launches there, the remaining interior launches on main
+// phase 5: the exchange is queued on st_edge; the first launch's edge zones there, the rest of the group on main
 int phase_jacobi_edges(natrix_sim* s, int sweeps) {
     const Geom& g = s->g;
     const bool up = g.y0 > 0, down = g.y0 + g.hl < g.hg;
     if (s->group_open != sweeps) return fail(NATRIX_ERR_STATE, "phase 5 must follow phase 4 with the same sweeps");
     const std::vector<int> depths = group_depths(sweeps, jacobi_launch_depth(s));
-    CU(cudaEventRecord(s->ev_xchg, s->st_edge));
-    CU(cudaStreamWaitEvent(s->st, s->ev_xchg, 0));
-    int src = s->pr, done = 0;
-    for (size_t j = 0; j < depths.size(); ++j) {
-        if (j > 0) CU(cudaStreamWaitEvent(s->st_edge, s->ev_int[j - 1], 0));
-        done += depths[j];
-        const bool pz = s->p_is_zero && j == 0;
-        if (up)
-            if (int rc = jacobi_rows(s, src, depths[j], s->ext_lo(sweeps - done), done, pz, s->st_edge)) return rc;
-        if (down)
-            if (int rc = jacobi_rows(s, src, depths[j], g.hl - done, s->ext_hi(sweeps - done), pz, s->st_edge)) return rc;
-        src = 1 - src;
-        if (j + 1 < depths.size())
-            if (int rc = interior_launch(s, depths, j + 1, src, done + depths[j + 1])) return rc;
-    }
+    int src = s->pr, done = depths[0];
+    if (up)
+        if (int rc = jacobi_rows(s, src, depths[0], s->ext_lo(sweeps - done), done, s->p_is_zero, s->st_edge)) return rc;
+    if (down)
+        if (int rc = jacobi_rows(s, src, depths[0], g.hl - done, s->ext_hi(sweeps - done), s->p_is_zero, s->st_edge)) return rc;
     CU(cudaEventRecord(s->ev_edges, s->st_edge));
     CU(cudaStreamWaitEvent(s->st, s->ev_edges, 0));
+    src = 1 - src;
+    for (size_t j = 1; j < depths.size(); ++j) {
+        done += depths[j];
+        if (int rc = jacobi_rows(s, src, depths[j], s->ext_lo(sweeps - done), s->ext_hi(sweeps - done), false, s->st)) return rc;
+        src = 1 - src;
+    }
     s->pr = src;
     s->p_is_zero = false;
     s->group_open = 0;
@@ -668,15 +652,31 @@ int step_slab(natrix_sim* s, float dt) {
     s->first_block = false;
     for (size_t i = 0; i < groups.size(); ++i) {
         const int t = groups[i];
-        if (overlap)
-            if (int rc = phase_jacobi_interior(s, t)) return rc;
         cudaStream_t xs = overlap ? s->st_edge : s->st;
+        if (overlap && s->xfirst) {
+            // the exchange kernel is queued BEFORE the interior launch and that launch leaves it `reserve` SMs:
+            // an interior launch is one wave of blocks that each own a whole SM, so an exchange queued behind it
+            // would only start when that wave drains
+            CU(cudaEventRecord(s->ev_group, s->st));
+            CU(cudaStreamWaitEvent(s->st_edge, s->ev_group, 0));
+        } else if (overlap) {
+            jacobi_tb_reserve_sms(s->tb, s->reserve_sms);
+            const int rc = phase_jacobi_interior(s, t);
+            jacobi_tb_reserve_sms(s->tb, 0);
+            if (rc) return rc;
+        }
         if (i == 0) {
             // p starts at zero, halos included - unless the simulator warm-starts from the last step's pressure
             const int first[3] = {NATRIX_DIVERGENCE, NATRIX_NBMASK, NATRIX_PRESSURE};
             if (int rc = exchange_fields(s, first, s->warm_start ? 3 : 2, std::min(span, n), xs)) return rc;
         } else {
             if (int rc = exchange_fields(s, &prs, 1, t, xs)) return rc;
+        }
+        if (overlap && s->xfirst) {
+            jacobi_tb_reserve_sms(s->tb, s->reserve_sms);
+            const int rc = phase_jacobi_interior(s, t);
+            jacobi_tb_reserve_sms(s->tb, 0);
+            if (rc) return rc;
         }
         if (int rc = overlap ? phase_jacobi_edges(s, t) : phase_jacobi(s, t)) return rc;
     }
@@ -784,8 +784,6 @@ int natrix_destroy(natrix_sim* s) {
     if (s->st_edge) { cudaStreamSynchronize(s->st_edge); cudaStreamDestroy(s->st_edge); }
     if (s->ev_group) cudaEventDestroy(s->ev_group);
     if (s->ev_edges) cudaEventDestroy(s->ev_edges);
-    if (s->ev_xchg) cudaEventDestroy(s->ev_xchg);
-    for (cudaEvent_t e : s->ev_int) cudaEventDestroy(e);
     if (s->st) cudaStreamDestroy(s->st);
     delete s;
     return 0;
@@ -982,6 +980,8 @@ int natrix_comm_init(natrix_sim* s, const void* id128, int rank, int world) {
     s->comm_rank = rank;
     s->comm_world = world;
     if (const char* e = getenv("NATRIX_SLAB_OVERLAP")) s->overlap = atoi(e) != 0;
+    if (const char* e = getenv("NATRIX_SLAB_XFIRST")) s->xfirst = atoi(e) != 0;
+    if (const char* e = getenv("NATRIX_SLAB_RESERVE")) s->reserve_sms = atoi(e);
     return 0;
 }
 
@@ -1068,8 +1068,7 @@ int natrix_copy_in(natrix_sim* s, int field, const void* host, size_t bytes) {
     CU(cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, s->st));
     CU(cudaStreamSynchronize(s->st));
     if (field == NATRIX_PRESSURE) s->p_is_zero = false;
-    if (field == NATRIX_NBMASK)
-        if (field == NATRIX_VELOCITY) CU(cudaMemsetAsync(s->d_err + 1, 1, s->nbands * sizeof(int), s->st));   // unknown range
+    if (field == NATRIX_VELOCITY) CU(cudaMemsetAsync(s->d_err + 1, 1, s->nbands * sizeof(int), s->st));   // unknown range
     return 0;
 }
 

@@ -360,6 +360,13 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
         tma_load_2d(d_addr + ((GROUP * g) & (D_ROWS - 1)) * (SW * 4), &map_d, x0, row, bar);
         tma_load_2d(m_addr + (g & (M_SLOTS - 1)) * M_SLOT, &map_m, x0 & ~15, row, bar);
     };
+    // Programmatic dependent launch: this grid may become resident while the previous kernel of the stream (the
+    // previous Jacobi launch, which wrote the pressure this one reads and read the buffer this one writes) is
+    // still draining; everything above touched no field.  Wait for that kernel's completion and memory flush,
+    // THEN let the next launch start its own prologue - so at most two launches are ever in flight and a launch
+    // never overtakes the readers of its output buffer.  Both are no-ops in a plain launch.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (lane == 0) issue(0);
 
     float a[PACKED ? 1 : T][2][4];                    // scalar state
@@ -727,6 +734,10 @@ struct JacobiTB {
     std::string trace_path;
     int trace_launch = 40, launch_no = 0;
     unsigned long long* d_trace = nullptr;
+    // programmatic dependent launch of consecutive Jacobi launches (NATRIX_TB_PDL=0 turns it off): the next
+    // launch's blocks take an SM as soon as this launch's block there has exited and wait in their prologue
+    int pdl = 1;
+    int reserve_sms = 0;          // SMs the next launches leave free (for an exchange kernel running beside them)
     bool attr_set[JACOBI_TB_MAX_DEPTH + 1][2][2][NUM_SHAPES] = {};
     int shape = 1;                // measured on B200 at 4096^2: 12 warps x 168 registers beats 2 x 8 warps x 128
 
@@ -775,6 +786,7 @@ JacobiTB* jacobi_tb_create() {
     if (const char* e = getenv("NATRIX_TB_KAPPA")) tb->kappa = atof(e);
     if (const char* e = getenv("NATRIX_TB_SIGMA")) tb->sigma = atof(e);
     if (const char* e = getenv("NATRIX_TB_L2PROMO")) tb->l2_promotion = atoi(e) & 3;
+    if (const char* e = getenv("NATRIX_TB_PDL")) tb->pdl = atoi(e) != 0;
     if (const char* e = getenv("NATRIX_TB_TRACE")) tb->trace_path = e;
     if (const char* e = getenv("NATRIX_TB_TRACE_LAUNCH")) tb->trace_launch = atoi(e);
     return tb;
@@ -785,6 +797,8 @@ void jacobi_tb_destroy(JacobiTB* tb) {
     for (auto& p : tb->plans) cudaFree(p.d_tiles);
     delete tb;
 }
+void jacobi_tb_reserve_sms(JacobiTB* tb, int n) { if (tb) tb->reserve_sms = n < 0 ? 0 : n; }
+
 const char* jacobi_tb_error(JacobiTB* tb) { return tb ? tb->err.c_str() : "null JacobiTB"; }
 
 int jacobi_tb_plan_debug(int w, int depth, int r0, int r1, const int* boxes, int nboxes, int max_tiles, int* out4,
@@ -831,7 +845,7 @@ int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div, const uin
     prm.r1 = r1;
     prm.hx = depth <= 4 ? 4 : 8;
     // one tile per resident warp; tile heights follow the obstacle boxes (see Plan)
-    const int max_tiles = tb->sm_count * warps * (tb->shape == 0 ? 2 : 1);
+    const int max_tiles = std::max(1, tb->sm_count - tb->reserve_sms) * warps * (tb->shape == 0 ? 2 : 1);
     // The grid's first and last row carry the B / T blocked bits (clamp-to-edge), so the rows next to them run
     // the select body while they are in flight: tell the planner (measured: the top band of tiles took 52.5 us
     // against 48 us for every other band at 4096^2).
@@ -859,8 +873,18 @@ int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div, const uin
         cudaMemsetAsync(tb->d_trace, 0, (size_t)prm.ntiles * 32, st);
         prm.trace = tb->d_trace;
     }
-    fn<<<blocks, warps * 32, smem, st>>>(map_p, map_d, map_m, prm);
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3((unsigned)(warps * 32));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (tb->pdl && !tracing) ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, map_p, map_d, map_m, prm);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { tb->err = std::string("k_jacobi_tb launch: ") + cudaGetErrorString(e); return -1; }
     if (tracing && prm.trace) {
         std::vector<unsigned long long> h((size_t)prm.ntiles * 4);

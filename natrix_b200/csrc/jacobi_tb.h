@@ -26,6 +26,10 @@ int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div, const uin
                      float* pout, Geom g, int depth, int r0, int r1, bool p_is_zero, int packed,
                      const int* boxes, int nboxes, cudaStream_t st);
 
+// The following launches leave n SMs without a block (0 = use every SM): room for a halo-exchange kernel that
+// runs beside an interior launch.
+void jacobi_tb_reserve_sms(JacobiTB* tb, int n);
+
 // Host-only: the tile plan jacobi_tb_launch would use for these arguments (no CUDA call), as
 // (strip, first row, end row, 0) quadruples; a strip is SW - 2*hx output columns wide, hx = 4 for depth <= 4
 // else 8.  Returns the number of tiles (which may exceed `cap`; only `cap` are written).  For tests.

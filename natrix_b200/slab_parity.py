@@ -31,6 +31,7 @@ def check(width: int, height: int, steps: int = 2, iterations: int = 37, local: 
     splats = [((0.5, 0.5), (0.9, -0.6), 48.0), ((0.2, 0.74), (-0.5, 0.8), 25.0)]
     mismatches, compared = [], 0
     combos = [(p, o, d) for p in pipelines for o in schedules for d in drivers]
+    driver_env = os.environ.get("NATRIX_SLAB_DRIVER")
     for pipeline, overlap, driver in combos:
         for _ in (0,):
             # native: the exchange inside libnatrix_b200.so (natrix_comm_init + natrix_step); python: the model of
@@ -87,6 +88,8 @@ def check(width: int, height: int, steps: int = 2, iterations: int = 37, local: 
             ref.destroy()
             slab.sim.destroy()
     os.environ.pop("NATRIX_SLAB_DRIVER", None)
+    if driver_env is not None:
+        os.environ["NATRIX_SLAB_DRIVER"] = driver_env
     flag = torch.tensor([len(mismatches)], device=f"cuda:{local}")
     dist.all_reduce(flag)
     return {"bit_identical": int(flag.item()) == 0, "grid": [width, height], "world": world, "steps": steps,

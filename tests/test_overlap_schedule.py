@@ -5,18 +5,18 @@ Every queued operation is listed with its stream, the rows of the two pressure b
 writes, the events it waits for and the event recorded behind it.  Two operations that touch the same
 rows of the same buffer, one of them writing, must be ordered by stream order or by an event - otherwise
 the slab result is no longer bit-identical to the single-GPU run.  The model also shows WHY the schedule
-has its three rules (negative cases): the second interior launch waits for the exchange, launch depths
-never decrease inside a group, and the next group waits for this group's edges.
+has its two waits (negative cases): the exchange waits for everything queued before the group, and the rest of
+the group waits for the first launch's edge zones (and through them for the exchange).
 """
 import itertools
 
 import pytest
 
 
-def group_depths(sweeps, depth, partial_first=True):
+def group_depths(sweeps, depth):
     full = [depth] * (sweeps // depth)
     part = [sweeps % depth] if sweeps % depth else []
-    return part + full if partial_first else full + part
+    return part + full
 
 
 class Schedule:
@@ -66,44 +66,38 @@ class Schedule:
         return out
 
 
-def build(groups, depth, hl, up=True, down=True, wait_exchange=True, partial_first=True, wait_edges=True):
-    """The operations of consecutive groups of `groups` sweeps on a slab of hl rows (api.cu, slabs.py)."""
+def build(groups, depth, hl, up=True, down=True, wait_edges=True, wait_group=True):
+    """The operations of consecutive groups of `groups` sweeps on a slab of hl rows (api.cu: phase_jacobi_interior,
+    phase_jacobi_edges; the exchange between them is queued by step_slab or by slabs.py)."""
     s = Schedule()
     src = 0
     s.op("main", "divergence / previous step", writes=[(0, -10**6, 10**6), (1, -10**6, 10**6)])
     for gi, t in enumerate(groups):
-        depths = group_depths(t, depth, partial_first)
+        depths = group_depths(t, depth)
         g = f"g{gi}"
+        d1 = depths[0]
         # phase 4: everything queued so far precedes the exchange and the edge zones
         s.op("main", f"{g} mark", record=f"{g}.group")
-        s.op("comm", f"{g} exchange", waits=[f"{g}.group"],
+        s.op("main", f"{g} I1", reads=[(src, 0 if up else -d1, hl if down else hl + d1)],
+             writes=[(1 - src, d1 if up else 0, hl - d1 if down else hl)])
+        s.op("comm", f"{g} exchange", waits=[f"{g}.group"] if wait_group else [],
              reads=([(src, 0, t)] if up else []) + ([(src, hl - t, hl)] if down else []),
-             writes=([(src, -t, 0)] if up else []) + ([(src, hl, hl + t)] if down else []), record=f"{g}.xchg")
-        done, cur = 0, src
-
-        def interior(j, cur, done):
-            d = depths[j]
-            lo, hi = (done if up else 0), (hl - done if down else hl)
-            waits = [f"{g}.xchg"] if (j == 1 and wait_exchange) else []
-            s.op("main", f"{g} I{j + 1}", waits=waits, reads=[(cur, lo - d, hi + d)], writes=[(1 - cur, lo, hi)],
-                 record=f"{g}.int{j}")
-
-        interior(0, cur, depths[0])
-        # phase 5
-        for j, d in enumerate(depths):
-            done += d
-            rem = t - done
-            waits = [f"{g}.int{j - 1}"] if j > 0 else []
-            if up:
-                s.op("comm", f"{g} B{j + 1} top", waits=waits, reads=[(cur, -rem - d, done + d)], writes=[(1 - cur, -rem, done)])
-            if down:
-                s.op("comm", f"{g} B{j + 1} bottom", waits=waits if not up else [],
-                     reads=[(cur, hl - done - d, hl + rem + d)], writes=[(1 - cur, hl - done, hl + rem)])
-            cur = 1 - cur
-            if j + 1 < len(depths):
-                interior(j + 1, cur, done + depths[j + 1])
+             writes=([(src, -t, 0)] if up else []) + ([(src, hl, hl + t)] if down else []))
+        # phase 5: the first launch's edge zones behind the exchange, the rest of the group in one piece on main
+        rem = t - d1
+        if up:
+            s.op("comm", f"{g} B1 top", reads=[(src, -rem - d1, d1 + d1)], writes=[(1 - src, -rem, d1)])
+        if down:
+            s.op("comm", f"{g} B1 bottom", reads=[(src, hl - d1 - d1, hl + rem + d1)], writes=[(1 - src, hl - d1, hl + rem)])
         s.op("comm", f"{g} edges done", record=f"{g}.edges")
         s.op("main", f"{g} join", waits=[f"{g}.edges"] if wait_edges else [])
+        cur, done = 1 - src, d1
+        for j, d in enumerate(depths[1:], start=2):
+            done += d
+            rem = t - done
+            lo, hi = (-rem if up else 0), (hl + rem if down else hl)
+            s.op("main", f"{g} F{j}", reads=[(cur, lo - d, hi + d)], writes=[(1 - cur, lo, hi)])
+            cur = 1 - cur
         src = cur
     s.op("main", "gradient", reads=[(src, -1, hl + 1)])
     return s
@@ -116,23 +110,21 @@ def test_overlapped_group_schedule_has_no_hazard(groups, depth, hl, up, down):
     assert build(groups, depth, hl, up, down).hazards() == []
 
 
-def test_interior_launches_really_run_beside_the_exchange():
+def test_the_first_interior_launch_really_runs_beside_the_exchange():
     s = build([48], 8, 4096)
     hb = s.happens_before()
     names = [o["name"] for o in s.ops]
-    i1, x = names.index("g0 I1"), names.index("g0 exchange")
-    assert not hb[i1][x] and not hb[x][i1]                       # the first interior launch overlaps the exchange
-    i3, b2 = names.index("g0 I3"), names.index("g0 B2 top")
-    assert not hb[i3][b2] and not hb[b2][i3]                     # later edge launches overlap interior launches
+    i1, x, b1 = names.index("g0 I1"), names.index("g0 exchange"), names.index("g0 B1 top")
+    assert not hb[i1][x] and not hb[x][i1]                       # the interior of the first launch overlaps the exchange
+    assert not hb[i1][b1] and not hb[b1][i1]                     # ... and the edge zones
+    assert hb[x][names.index("g0 F2")] and hb[b1][names.index("g0 F2")]
 
 
 def test_the_rules_of_the_schedule_are_all_needed():
-    # without the wait, I2 overwrites rows of the buffer the exchange is still sending from (the bug that
-    # showed up as 1-ulp differences in the neighbour's pressure)
-    bad = build([24, 24], 8, 2048, wait_exchange=False).hazards()
-    assert any({"g1 exchange", "g1 I2"} == {a, b} for a, b, *_ in bad)
-    # a partial launch at the END of a group lets an edge launch read rows the next interior launch writes
-    bad = build([20], 8, 2048, partial_first=False).hazards()
-    assert any("B2" in a + b and "I3" in a + b for a, b, *_ in bad)
-    # the next group must wait for this group's edges
-    assert build([24, 24], 8, 2048, wait_edges=False).hazards()
+    # the rest of the group writes the buffer the exchange sends from and the edge zones read: without the wait
+    # for the edges it races with both
+    bad = build([24, 24], 8, 2048, wait_edges=False).hazards()
+    assert any({a, b} == {"g0 exchange", "g0 F2"} for a, b, *_ in bad) and any("B1" in a + b and "F2" in a + b for a, b, *_ in bad)
+    # the exchange must wait for everything queued before the group (it sends rows the previous group wrote)
+    bad = build([24, 24], 8, 2048, wait_group=False).hazards()
+    assert any("g1 exchange" in (a, b) and ("g0 F3" in (a, b) or "g0 F2" in (a, b)) for a, b, *_ in bad)
