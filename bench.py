@@ -357,10 +357,14 @@ def measure_single_gpu(args, w: W.Workload, with_cpu: bool, steps: int):
                 "note": "public Python API per step; inputs are the host-side impulse / obstacle parameters, the "
                         "result read back each step is the (sum, sumsq, min, max) of the velocity field"},
         "gpu_launches": int(launches), "clocks": clocks,
+        "plan_cache": dict(zip(("hits", "misses"), sim.plan_cache_stats())),
         "so": L.loaded_library_path(),
     }
     sim.destroy()
     return line
+
+
+SUB_KEYS = ("value", "unit", "ms_per_step", "config", "stage_ms", "roofline", "stages_roofline", "e2e", "gpu_launches", "plan_cache")
 
 
 def run_single_gpu(args, w: W.Workload, secondary=None):
@@ -368,8 +372,16 @@ def run_single_gpu(args, w: W.Workload, secondary=None):
     if secondary is not None:
         # the 4096^2 configuration the metric also quotes, measured in the same run
         sub = measure_single_gpu(args, secondary, with_cpu=False, steps=max(args.steps, 20))
-        line["config3_4096"] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "config", "stage_ms", "roofline", "stages_roofline", "e2e",
-                                                     "gpu_launches")}
+        line["config3_4096"] = {k: sub[k] for k in SUB_KEYS}
+        # config 5 with the 64 circles drifting 3 cells per step: a new obstacle set - and a new tile plan for the
+        # Jacobi kernel - every step (the static workload re-adds identical circles and always hits the plan cache)
+        import dataclasses
+        moving = dataclasses.replace(w, name=w.name + "-moving", drift=3.0)
+        sub = measure_single_gpu(args, moving, with_cpu=False, steps=min(args.steps, 10))
+        line["config5_moving"] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "stage_ms", "e2e", "gpu_launches", "plan_cache")}
+        # the 1-GPU point of config 4 (16384^2, strong scaling; the N > 1 lines carry `config4_strong`)
+        sub = measure_single_gpu(args, W.cfg4_workload(16384), with_cpu=False, steps=min(args.steps, 10))
+        line["config4_16384"] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "config", "stage_ms", "e2e", "gpu_launches")}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -380,7 +392,7 @@ def main(argv=None):
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="natrix_b200", choices=["natrix_b200", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "demo", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "demo", "cfg2", "cfg3", "cfg4", "cfg5", "cfg5m"])
     ap.add_argument("--size", type=int, default=None, help="override the grid size of cfg3/cfg4")
     ap.add_argument("--pipeline", type=int, default=None)
     ap.add_argument("--depth", type=int, default=None)
@@ -411,6 +423,8 @@ def main(argv=None):
         w = W.cfg4_workload(args.size or 16384)
     else:
         w = W.cfg5_workload(n)
+        if name == "cfg5m":
+            w.name, w.drift = w.name + "-moving", 3.0
 
     if args.no_obstacles:
         w.circles = []

@@ -208,6 +208,9 @@ int natrix_launch_count(natrix_sim* sim, unsigned long long* kernels);
  * columns wide.  Returns the number of tiles.  Results of a step never depend on the plan. */
 int natrix_debug_plan_tiles(int width, int depth, int row0, int row1, const int* boxes, int nboxes,
                             int max_tiles, int* out4, int cap);
+/* Tile-plan cache of the temporally blocked Jacobi kernel: launches that reused a plan / that cut and uploaded a
+ * new one (a new obstacle set; asynchronous, no allocation on the step path). */
+int natrix_debug_plan_stats(natrix_sim* sim, unsigned long long* hits, unsigned long long* misses);
 const char* natrix_last_error(void);
 const char* natrix_version(void);
 

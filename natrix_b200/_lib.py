@@ -62,6 +62,7 @@ SIGNATURES = {
     "natrix_get_timings": (_i, [_vp, _pf, _i]),
     "natrix_launch_count": (_i, [_vp, C.POINTER(C.c_ulonglong)]),
     "natrix_debug_plan_tiles": (_i, [_i, _i, _i, _i, _pi, _i, _i, _pi, _i]),
+    "natrix_debug_plan_stats": (_i, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "natrix_last_error": (C.c_char_p, []),
     "natrix_version": (C.c_char_p, []),
 }

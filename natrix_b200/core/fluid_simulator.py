@@ -304,6 +304,12 @@ class FluidSimulator:
         L.check(self._lib.natrix_get_timings(self._handle(), ms, 6))
         return dict(zip(("advect", "forces", "divergence", "jacobi", "gradient", "clear"), ms))
 
+    def plan_cache_stats(self):
+        """(hits, misses) of the Jacobi kernel's tile-plan cache (a miss = a new obstacle set)."""
+        h, m = C.c_ulonglong(), C.c_ulonglong()
+        L.check(self._lib.natrix_debug_plan_stats(self._handle(), C.byref(h), C.byref(m)))
+        return h.value, m.value
+
     @property
     def launch_count(self) -> int:
         out = C.c_ulonglong()

@@ -1361,6 +1361,12 @@ int natrix_debug_plan_tiles(int width, int depth, int row0, int row1, const int*
     return jacobi_tb_plan_debug(width, depth, row0, row1, boxes, nboxes, max_tiles, out4, cap);
 }
 
+int natrix_debug_plan_stats(natrix_sim* s, unsigned long long* hits, unsigned long long* misses) {
+    NEED(s && hits && misses, "null argument");
+    jacobi_tb_plan_stats(s->tb, hits, misses);
+    return 0;
+}
+
 int natrix_launch_count(natrix_sim* s, unsigned long long* kernels) {
     NEED(s && kernels, "null argument");
     *kernels = s->launches;

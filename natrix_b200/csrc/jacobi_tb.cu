@@ -524,7 +524,6 @@ struct JacobiTB {
         std::vector<int4> tiles;
         int4* d_tiles = nullptr;
     };
-    std::vector<Plan> plans;
     double sigma = 1.0;
     // measured (ncu, 32768x4096): 256 B promotion fetches 7 % more DRAM bytes than 128 B / none for the same time
     int l2_promotion = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;      // NATRIX_TB_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B
@@ -710,24 +709,86 @@ struct JacobiTB {
         return tiles;
     }
 
+    // Plan cache without a cliff.  Per launching stream, SLOTS fixed-size slots in one device arena with a pinned
+    // host mirror, allocated on first use.  A miss (a new obstacle set - every step when obstacles move) costs the
+    // host-side cut and an asynchronous upload on the launching stream: no cudaMalloc, no stream synchronisation
+    // and no cudaFree on the step path.  A slot is only ever read by launches on its own stream, so overwriting
+    // the least recently used one is ordered behind its readers by the stream itself; the pinned mirror of the
+    // slot is guarded by an event recorded behind its previous upload (long complete unless the host has run more
+    // than SLOTS misses ahead of the GPU).
+    static constexpr int SLOTS = 32;
+    struct Pool {
+        cudaStream_t stream = nullptr;
+        int slot_cap = 0;                          // tiles per slot
+        int4* d_arena = nullptr;
+        int4* h_arena = nullptr;
+        std::vector<Plan> plans;
+        cudaEvent_t uploaded[SLOTS] = {};
+        unsigned long long used[SLOTS] = {};
+    };
+    std::vector<Pool*> pools;
+    unsigned long long use_clock = 0, plan_hits = 0, plan_misses = 0;
+
     const Plan* plan_for(int w, int r0, int r1, int hx, int depth, const int* boxes, int nboxes, int max_tiles,
                          int warps_per_block, cudaStream_t st) {
         std::vector<int> key = {w, r0, r1, hx, depth, max_tiles, chunk_override, warps_per_block};
         key.insert(key.end(), boxes, boxes + 4 * nboxes);
-        for (const Plan& p : plans)
-            if (p.key == key) return &p;
-        Plan p;
-        p.key = key;
-        p.tiles = cut_tiles(w, r0, r1, hx, depth, boxes, nboxes, max_tiles, kappa, chunk_override, sigma, warps_per_block);
-        if (cudaMalloc((void**)&p.d_tiles, p.tiles.size() * sizeof(int4)) != cudaSuccess) { err = "cudaMalloc(tile plan)"; return nullptr; }
-        if (cudaMemcpyAsync(p.d_tiles, p.tiles.data(), p.tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, st) != cudaSuccess ||
-            cudaStreamSynchronize(st) != cudaSuccess) { err = "tile plan upload failed"; cudaFree(p.d_tiles); return nullptr; }
-        if (plans.size() >= 128) {                // evict the oldest; the stream is idle after the sync above
-            cudaFree(plans.front().d_tiles);
-            plans.erase(plans.begin());
+        Pool* pool = nullptr;
+        for (Pool* q : pools)
+            if (q->stream == st) pool = q;
+        if (!pool) {
+            pool = new Pool();
+            pool->stream = st;
+            pool->plans.resize(SLOTS);
+            pools.push_back(pool);
         }
-        plans.push_back(std::move(p));
-        return &plans.back();
+        for (int i = 0; i < SLOTS; ++i) {
+            Plan& p = pool->plans[i];
+            if (p.d_tiles && p.key == key) {
+                pool->used[i] = ++use_clock;
+                ++plan_hits;
+                return &p;
+            }
+        }
+        ++plan_misses;
+        std::vector<int4> tiles = cut_tiles(w, r0, r1, hx, depth, boxes, nboxes, max_tiles, kappa, chunk_override, sigma, warps_per_block);
+        const int pitch = SW - 2 * hx, nstrips = (w + pitch - 1) / pitch;
+        const int need = std::max((int)tiles.size(), sm_count * 32 + 2 * nstrips);
+        if (need > pool->slot_cap) {
+            // (re)allocate the arena: first use, or more tiles than any plan before (not the steady state)
+            cudaStreamSynchronize(st);
+            cudaFree(pool->d_arena);
+            if (pool->h_arena) cudaFreeHost(pool->h_arena);
+            pool->d_arena = nullptr; pool->h_arena = nullptr;
+            pool->slot_cap = need + need / 4;
+            if (cudaMalloc((void**)&pool->d_arena, (size_t)SLOTS * pool->slot_cap * sizeof(int4)) != cudaSuccess ||
+                cudaMallocHost((void**)&pool->h_arena, (size_t)SLOTS * pool->slot_cap * sizeof(int4)) != cudaSuccess) {
+                err = "tile plan arena allocation failed";
+                return nullptr;
+            }
+            for (int i = 0; i < SLOTS; ++i) {
+                pool->plans[i] = Plan();
+                pool->used[i] = 0;
+                if (!pool->uploaded[i] && cudaEventCreateWithFlags(&pool->uploaded[i], cudaEventDisableTiming) != cudaSuccess) {
+                    err = "cudaEventCreate(tile plan)";
+                    return nullptr;
+                }
+            }
+        }
+        int victim = 0;
+        for (int i = 1; i < SLOTS; ++i)
+            if (pool->used[i] < pool->used[victim]) victim = i;
+        Plan& p = pool->plans[victim];
+        if (p.d_tiles && cudaEventSynchronize(pool->uploaded[victim]) != cudaSuccess) { err = "cudaEventSynchronize(tile plan)"; return nullptr; }
+        p.key = std::move(key);
+        p.tiles = std::move(tiles);
+        p.d_tiles = pool->d_arena + (size_t)victim * pool->slot_cap;
+        int4* host = pool->h_arena + (size_t)victim * pool->slot_cap;
+        std::copy(p.tiles.begin(), p.tiles.end(), host);
+        if (cudaMemcpyAsync(p.d_tiles, host, p.tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaEventRecord(pool->uploaded[victim], st) != cudaSuccess) { err = "tile plan upload failed"; return nullptr; }
+        pool->used[victim] = ++use_clock;
+        return &p;
     }
     // developer tracing: NATRIX_TB_TRACE=<file> dumps per-tile (strip, rows, start, end, SM) of launch number
     // NATRIX_TB_TRACE_LAUNCH (default 40) as CSV; costs a device sync on that launch only
@@ -794,8 +855,17 @@ JacobiTB* jacobi_tb_create() {
 
 void jacobi_tb_destroy(JacobiTB* tb) {
     if (!tb) return;
-    for (auto& p : tb->plans) cudaFree(p.d_tiles);
+    for (JacobiTB::Pool* q : tb->pools) {
+        cudaFree(q->d_arena);
+        if (q->h_arena) cudaFreeHost(q->h_arena);
+        for (cudaEvent_t e : q->uploaded) if (e) cudaEventDestroy(e);
+        delete q;
+    }
     delete tb;
+}
+void jacobi_tb_plan_stats(JacobiTB* tb, unsigned long long* hits, unsigned long long* misses) {
+    *hits = tb ? tb->plan_hits : 0;
+    *misses = tb ? tb->plan_misses : 0;
 }
 void jacobi_tb_reserve_sms(JacobiTB* tb, int n) { if (tb) tb->reserve_sms = n < 0 ? 0 : n; }
 

@@ -30,6 +30,9 @@ int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div, const uin
 // runs beside an interior launch.
 void jacobi_tb_reserve_sms(JacobiTB* tb, int n);
 
+// Tile-plan cache counters: launches that found their plan / that had to cut and upload a new one.
+void jacobi_tb_plan_stats(JacobiTB* tb, unsigned long long* hits, unsigned long long* misses);
+
 // Host-only: the tile plan jacobi_tb_launch would use for these arguments (no CUDA call), as
 // (strip, first row, end row, 0) quadruples; a strip is SW - 2*hx output columns wide, hx = 4 for depth <= 4
 // else 8.  Returns the number of tiles (which may exceed `cap`; only `cap` are written).  For tests.

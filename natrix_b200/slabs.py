@@ -353,6 +353,77 @@ class SlabSmoothParticlesArea:
 
 
 # ----------------------------------------------------------------------------------------- bench
+def strong_scaling_point(args, w, local: int, depth: int, metric: str) -> dict:
+    """Workload `w` (one fixed grid) on all ranks as row slabs, and on one GPU alone; device-timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from natrix_b200 import _lib as L
+    from natrix_b200 import workloads as W
+    from natrix_b200.core.fluid_simulator import FluidSimulator
+
+    import time
+
+    world = dist.get_world_size()
+    steps = max(3, min(args.steps, 10))
+
+    def timed(sim, stream, one_step, synchronize):
+        for k in range(3):
+            one_step(k)
+        synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for k in range(steps):
+            one_step(3 + k)
+        host = 1e3 * (time.perf_counter() - t0) / steps
+        synchronize()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=f"cuda:{local}")
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), host
+
+    slab = SlabSimulator(w.width, w.height, device=local, depth=depth)
+    W.configure(slab.sim, w)
+    slab.iterations = w.iterations
+    slab.sim.set_option(L.OPT_JACOBI_DEPTH, depth)
+    slab.sim.upload("velocity", W.smooth_velocity(w.width, w.height, slab.row0, slab.rows))
+    dye = None
+    if w.dye_size:
+        dye = SlabSmoothParticlesArea(w.dye_size[0], w.dye_size[1], slab)
+        dye.dissipation = w.dye_dissipation
+
+    def slab_step(k):
+        for (px, py, r) in W.circles_at(w, k):
+            slab.add_circle_obstacle((px, py), r)
+        slab.update(W.DT)
+        if dye is not None:
+            dye.update(W.DT)
+        for (px, py, vx, vy) in W.orbit_positions(w, k):
+            slab.add_velocity((px, py), (vx, vy), w.splat_radius)
+            if dye is not None:
+                dye.add_particles((px, py), w.dye_radius, w.dye_strength)
+
+    ms_n, host_n = timed(slab.sim, slab.engine.stream, slab_step, slab.sim.synchronize)
+    native = slab.native
+    slab.sim.destroy()
+    from natrix_b200.smooth_particles_area import SmoothParticlesArea
+    solo, solo_dye = W.build(w, FluidSimulator, SmoothParticlesArea if w.dye_size else None, device=local)
+    solo.set_option(L.OPT_JACOBI_DEPTH, depth)
+    ms_1, _ = timed(solo, torch.cuda.ExternalStream(solo.cuda_stream, device=local), lambda k: W.run_step(w, solo, solo_dye, k),
+                    solo.synchronize)
+    solo.destroy()
+    v_n, v_1 = w.cells / (ms_n * 1e-3) / 1e6, w.cells / (ms_1 * 1e-3) / 1e6
+    return {"workload": w.name, "grid": [w.width, w.height], "dye_grid": list(w.dye_size) if w.dye_size else None,
+            "jacobi_iterations": w.iterations, "scaling": "strong",
+            "n_gpus": world, "value": v_n, "unit": metric, "ms_per_step": ms_n, "host_enqueue_ms_per_step": host_n,
+            "one_gpu": {"value": v_1, "ms_per_step": ms_1, "note": "the same grid on one GPU of this box (every rank, max)"},
+            "efficiency": v_n / (world * v_1), "steps": steps, "driver": "native" if native else "python"}
+
+
 def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
     """bench.py --gpus N under torchrun: weak scaling, one 32768 x 4096 slab per rank."""
     import json
@@ -391,7 +462,7 @@ def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
         dye.dissipation = w.dye_dissipation
 
     def one_step(k):                                  # the demo's call order, as workloads.run_step
-        for (px, py, r) in w.circles:
+        for (px, py, r) in W.circles_at(w, k):
             slab.add_circle_obstacle((px, py), r)
         slab.update(W.DT)
         if dye is not None:
@@ -465,6 +536,16 @@ def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
     base_value = w1.cells / (float(bms.item()) * 1e-3) / 1e6
     solo.destroy()
 
+    # config 4 (BASELINE.json): 16384^2 STRONG scaling - the same grid cut into `world` slabs, against the same grid
+    # on one GPU of this box (every rank runs it standalone, max over ranks), measured in this run
+    strong = dye_point = None
+    n_exchanges, n_bytes = slab.exchanges, slab.exchanged_bytes
+    if getattr(args, "workload", "auto") == "auto":
+        slab.sim.destroy()
+        strong = strong_scaling_point(args, W.cfg4_workload(16384), local, depth, metric)
+        # ... and config 3 (4096^2 velocity + 4096^2 dye, splats) on the same slabs: the dye field's own exchange
+        dye_point = strong_scaling_point(args, W.cfg3_workload(4096), local, depth, metric)
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         algo = jacobi_bytes * w.cells * w.iterations + (116 if w.viscosity == 0 else 132) * w.cells
@@ -482,10 +563,10 @@ def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
                        "algorithmic_GBps_per_gpu": algo / world / (ms_per_step * 1e-3) / 1e9},
             "weak_base": {"workload": w1.name, "n_gpus": 1, "value": base_value, "ms_per_step": float(bms.item()),
                           "note": "same per-GPU slab run standalone on every rank of this box (max over ranks)"},
-            "slab_parity": parity,
+            "slab_parity": parity, "config4_strong": strong, "config3_dye_slabs": dye_point,
             "halo": {"driver": "libnatrix_b200.so (natrix_step: NCCL send/recv from C)" if slab.native else "python (torch.distributed)",
-                     "exchanges_per_step": slab.exchanges / (2 * args.steps + max(args.warmup, 3)),
-                     "bytes_per_exchange": slab.exchanged_bytes / max(slab.exchanges, 1),
+                     "exchanges_per_step": n_exchanges / (2 * args.steps + max(args.warmup, 3)),
+                     "bytes_per_exchange": n_bytes / max(n_exchanges, 1),
                      "host_enqueue_ms_per_step": host_ms},
             "e2e": {"value": w.cells / (float(e2e_ms.item()) * 1e-3) / 1e6, "unit": metric,
                     "ms_per_step": float(e2e_ms.item()), "h2d_bytes_per_step": 16 * len(w.circles) + 32,

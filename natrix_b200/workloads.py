@@ -34,6 +34,7 @@ class Workload:
     dye_strength: float = 0.04
     orbit_seed: Optional[int] = None
     init: str = "zero"                   # "zero" | "smooth" | "random"
+    drift: float = 0.0                   # cells per step the obstacles move along +x (wrapping): a new obstacle set every step
 
     @property
     def cells(self) -> int:
@@ -154,10 +155,17 @@ def orbit_positions(w: Workload, step: int) -> List[Tuple[float, float, float, f
     return out
 
 
+def circles_at(w: Workload, step: int) -> List[Tuple[float, float, float]]:
+    """The obstacles of one step: fixed, or (w.drift != 0) moved along +x by `drift` cells per step, wrapping."""
+    if not w.drift:
+        return w.circles
+    return [((px + step * w.drift / w.width) % 1.0, py, r) for (px, py, r) in w.circles]
+
+
 def run_step(w: Workload, sim, dye, step: int, dt: float = DT) -> None:
     """One frame in the demo's call order (simulation_demo.py:220-237): obstacles ->
     fluid.update -> dye.update -> impulses."""
-    for (px, py, r) in w.circles:
+    for (px, py, r) in circles_at(w, step):
         sim.add_circle_obstacle((px, py), r)
     sim.update(dt)
     if dye is not None:

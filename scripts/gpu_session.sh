@@ -1,18 +1,12 @@
 set -u
-OUT=gpurun_out/r2i; mkdir -p $OUT
+OUT=gpurun_out/r2j; mkdir -p $OUT
 timeout 1200 python -m pytest tests -m gpu -q -x > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/pytest_gpu.log
-run() { # name, env...
-  local name=$1; shift
-  env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 > $OUT/bench_n2_$name.json 2> $OUT/bench_n2_$name.err; echo "bench $name rc=$?"
-  python - $OUT/bench_n2_$name.json $name <<'PY'
+timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; tail -3 $OUT/bench.err
+python - $OUT/bench.json <<'PY'
 import json, sys
-l = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-print(sys.argv[2], round(l["value"]), round(l["ms_per_step"], 3), "base", round(l["weak_base"]["ms_per_step"], 3), "eff", round(l["value"] / (2 * l["weak_base"]["value"]), 4), "e2e", round(l["e2e"]["ms_per_step"], 3), l["halo"], "parity", l["slab_parity"]["bit_identical"])
+d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print("cfg5", round(d["value"]), round(d["ms_per_step"], 3), d["stage_ms"], "e2e", round(d["e2e"]["value"]), d["plan_cache"], "cpu", d["cpu_baseline"])
+for k in ("config3_4096", "config5_moving", "config4_16384"):
+    s = d[k]; print(k, round(s["value"]), round(s["ms_per_step"], 3), s["stage_ms"], "e2e", round(s["e2e"]["value"]), s.get("plan_cache"))
 PY
-}
-run default A=1
-run xfirst_r2 NATRIX_SLAB_XFIRST=1 NATRIX_SLAB_RESERVE=2
-run xfirst_r8 NATRIX_SLAB_XFIRST=1 NATRIX_SLAB_RESERVE=8
-run xfirst_r2_cta2 NATRIX_SLAB_XFIRST=1 NATRIX_SLAB_RESERVE=2 NCCL_MAX_CTAS=2
-run nooverlap NATRIX_SLAB_OVERLAP=0
-run python NATRIX_SLAB_DRIVER=python
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref rc=$?"; cut -c1-600 $OUT/bench_ref.json

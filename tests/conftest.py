@@ -17,7 +17,7 @@ def pytest_sessionstart(session):
     """The shared libraries are build artefacts (git-ignored): on a fresh checkout build them once (nvcc
     cross-compiles for sm_100a without a GPU), exactly as __graft_entry__.build() does."""
     missing = [p for p in (ROOT / "natrix_b200" / "libnatrix_b200.so", ROOT / "oracle" / "_build" / "libnatrix_oracle.so",
-                           ROOT / "examples" / "_build" / "c_host") if not p.exists()]
+                           ROOT / "examples" / "_build" / "c_host", ROOT / "examples" / "_build" / "c_host_multi") if not p.exists()]
     if missing:
         import __graft_entry__
 

@@ -28,3 +28,20 @@ def test_slabs_bit_identical_to_single_gpu(world, overlap):
     env = dict(os.environ, NATRIX_SLAB_OVERLAP=str(overlap))
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0 and "SLAB_CHECK PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_pure_c_multi_gpu_host_is_bit_identical_to_single_gpu():
+    """examples/c_host_multi.c: two host threads, two slab handles, natrix_comm_init + natrix_step - no Python and no
+    torch in the process; every slab's velocity, pressure and dye rows equal the single-GPU run's byte for byte."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = ROOT / "examples" / "_build" / "c_host_multi"
+    if not exe.exists():
+        pytest.skip("examples/_build/c_host_multi is not built (python -c 'import __graft_entry__ as g; g.build()')")
+    import torch
+    nccl = os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "nccl", "lib", "libnccl.so.2")
+    env = dict(os.environ)
+    if os.path.exists(nccl):
+        env["NATRIX_NCCL_LIB"] = nccl                      # the same NCCL the Python path uses
+    res = subprocess.run([str(exe), "2", "6"], capture_output=True, text=True, timeout=300, env=env)
+    assert res.returncode == 0 and "C_HOST_MULTI PASS" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]

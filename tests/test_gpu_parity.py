@@ -394,6 +394,29 @@ def test_config5_slab_size_fused_equals_reference_order_pipeline():
         del fa, fb
 
 
+def test_moving_obstacles_every_step_a_new_tile_plan_vs_oracle():
+    """Obstacles that move every step give the Jacobi kernel a new tile plan every step: 40 steps on a 512 x 256 grid
+    walk through more plans than the cache has slots (cut + asynchronous upload + slot reuse on the step path).
+    Every field of the last step and a few on the way, bit for bit against the oracle."""
+    import dataclasses
+    w = W.Workload("moving-512x256", 512, 256, 17, 1.0, 0.1, circles=[(0.2, 0.3, 18.0), (0.6, 0.7, 30.0), (0.9, 0.5, 12.0)],
+                   splats_per_step=1, splat_radius=20.0, init="random", drift=5.0)
+    g, _ = W.build(w, _sim_cls(1), None)
+    o, _ = W.build(w, OracleFluidSimulator, None)
+    for k in range(40):
+        W.run_step(w, g, None, k)
+        W.run_step(w, o, None, k)
+        if k in (0, 7, 39):
+            assert_fields_close(W.fields_of(g), W.fields_of(o), exact=True)
+    hits, misses = g.plan_cache_stats()
+    assert misses >= 40 and hits >= 40, (hits, misses)          # a new plan per step, reused by the step's later launches
+    static = dataclasses.replace(w, drift=0.0)
+    g2, _ = W.build(static, _sim_cls(1), None)
+    for k in range(5):
+        W.run_step(static, g2, None, k)
+    assert g2.plan_cache_stats()[1] <= 4                        # the same circles every step: the plans are found again
+
+
 def test_headless_demo_writes_frames(tmp_path):
     """the headless replay of the demo loop produces PNG frames that are not blank."""
     from natrix_b200.headless_demo import run
