@@ -63,7 +63,12 @@ enum natrix_option {
     NATRIX_OPT_TIMING = 2,   /* 1 = record per-stage CUDA events (natrix_get_timings)        */
     NATRIX_OPT_WARM_START = 3, /* NOT reference behaviour, default 0: 1 = keep the previous
                                 step's pressure as the initial guess instead of clearing it            */
-    NATRIX_OPT_PACKED = 4    /* 1 = f32x2 packed arithmetic in the Jacobi kernel              */
+    NATRIX_OPT_PACKED = 4,   /* 1 = f32x2 packed arithmetic in the Jacobi kernel              */
+    NATRIX_OPT_JACOBI_KERNEL = 5, /* which temporally blocked kernel runs the sweeps of pipeline 1: 0 = auto (default:
+                                shared-memory tiles for small, latency-bound grids and for widths TMA cannot
+                                address, register streaming behind TMA otherwise), 1 = TMA kernel, 2 = shared-memory
+                                kernel.  natrix_get_option reports the kernel in use (1 or 2; 0 under pipeline 0) */
+    NATRIX_OPT_SMEM_DEPTH = 6 /* sweeps per launch of the shared-memory Jacobi kernel, 1..16 (default 16)  */
 };
 
 /* ---- lifetime ------------------------------------------------------------------------

@@ -15,7 +15,7 @@ LIB_PATH = _PKG / "libnatrix_b200.so"
 
 # enum natrix_field / natrix_option (include/natrix_b200.h)
 VELOCITY, PRESSURE, DIVERGENCE, VORTICITY, OBSTACLES, NBMASK = range(6)
-OPT_PIPELINE, OPT_JACOBI_DEPTH, OPT_TIMING, OPT_WARM_START, OPT_PACKED = range(5)
+OPT_PIPELINE, OPT_JACOBI_DEPTH, OPT_TIMING, OPT_WARM_START, OPT_PACKED, OPT_JACOBI_KERNEL, OPT_SMEM_DEPTH = range(7)
 
 FIELD_COMPONENTS = {VELOCITY: 2, PRESSURE: 1, DIVERGENCE: 1, VORTICITY: 1, OBSTACLES: 2, NBMASK: 1}
 

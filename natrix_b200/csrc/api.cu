@@ -9,6 +9,7 @@
 #include <vector>
 
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX 3: a few ns per call unless a profiler is attached
 
 #include "kernels.h"
 #include "jacobi_tb.h"
@@ -81,6 +82,12 @@ Nccl* nccl() {
             return fail(NATRIX_ERR_CUDA, std::string(#expr) + ": " + nccl()->GetErrorString(r__)); \
     } while (0)
 
+// NVTX range around one stage of the step (tracing); shows up per stage in Nsight Systems / ncu --nvtx
+struct Range {
+    explicit Range(const char* name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+};
+
 enum Stage { ST_ADVECT = 0, ST_VORT, ST_DIV, ST_JACOBI, ST_GRAD, ST_CLEAR, ST_COUNT };
 
 }  // namespace
@@ -106,6 +113,8 @@ struct natrix_sim {
     int iterations = 50, has_borders = 1, viscous = 1;
     // options
     int pipeline = 1, jacobi_depth = 8, timing = 0, packed = 1, warm_start = 0;
+    int jacobi_kernel = 0;                       // NATRIX_OPT_JACOBI_KERNEL: 0 auto, 1 TMA register streaming, 2 shared memory
+    int smem_depth = 0;                          // sweeps per launch of the shared-memory kernel (set at create)
     // bookkeeping
     std::vector<SplatV> pending;                 // add_velocity calls not yet applied (pipeline 1)
     std::vector<float> circles;                  // queued add_circle_obstacle calls (sx, sy, r), pipeline 1
@@ -231,6 +240,7 @@ void stamp(natrix_sim* s, int i) {
 
 // apply queued add_velocity calls in one pass (pipeline 1) - identical per-cell arithmetic
 int flush_splats(natrix_sim* s) {
+    Range nvtx_range("natrix.add_velocity");
     size_t i = 0;
     const int lo = s->ext_lo(s->g.halo), hi = s->ext_hi(s->g.halo);
     while (i < s->pending.size()) {
@@ -318,6 +328,7 @@ int check_range_flag(natrix_sim* s, bool wait) {
 
 // ---- the four phases of a step -------------------------------------------------------------
 int phase_advect(natrix_sim* s, float dt) {
+    Range nvtx_range("natrix.pre_projection");
     const Geom& g = s->g;
     if (int rc = flush_splats(s)) return rc;
     if (int rc = flush_circles(s)) return rc;
@@ -358,13 +369,9 @@ int phase_forces(natrix_sim* s, float dt) {
     s->first_block = true;
     if (s->fused_pre) {
         stamp(s, ST_DIV);
-        // clear pressure (fluid_simulator.py:236-248): the first temporally blocked launch treats p as
-        // zero without reading it, so the fill itself is only needed for the 1-sweep fallback kernel.
+        // clear pressure (fluid_simulator.py:236-248): the first temporally blocked launch (either kernel) treats
+        // p as zero without reading it, so no fill is needed.
         // NATRIX_OPT_WARM_START keeps the previous step's pressure as the initial guess instead.
-        if (!s->warm_start && !jacobi_tb_supported(g)) {
-            CU(cudaMemsetAsync(s->p_base[s->pr], 0, s->cells_alloc * sizeof(float), s->st));
-            s->launches += 1;
-        }
         s->p_is_zero = !s->warm_start;
         return 0;
     }
@@ -390,6 +397,23 @@ int phase_forces(natrix_sim* s, float dt) {
     return 0;
 }
 
+// Which temporally blocked kernel runs the sweeps of pipeline 1: the shared-memory one (jacobi_smem.cu) for
+// grids small enough to be latency-bound and for widths TMA cannot address, else the register-streaming TMA
+// kernel (jacobi_tb.cu).  NATRIX_OPT_JACOBI_KERNEL forces either (tests, A/B measurements).
+bool use_smem_kernel(const natrix_sim* s) {
+    if (s->pipeline == 0) return false;
+    if (s->jacobi_kernel == 2 || !jacobi_tb_supported(s->g)) return true;
+    if (s->jacobi_kernel == 1) return false;
+    return s->g.hl == s->g.hg && s->cells_alloc <= jacobi_smem_cell_limit();
+}
+
+int jacobi_launch_depth(const natrix_sim* s) {
+    if (s->pipeline == 0) return 1;
+    if (use_smem_kernel(s))      // slabs keep one depth for both kernels: the exchange schedule is built on it
+        return s->g.hl == s->g.hg ? s->smem_depth : std::min(s->smem_depth, s->jacobi_depth);
+    return s->jacobi_depth;
+}
+
 // `sweeps` Jacobi sweeps; requires p, div, nbmask valid on ext(sweeps) (exchange done by caller)
 // One launch of `depth` Jacobi sweeps over local rows [r0, r1): p[src] -> p[1 - src] on stream st.
 int jacobi_rows(natrix_sim* s, int src, int depth, int r0, int r1, bool p_zero, cudaStream_t st) {
@@ -397,9 +421,11 @@ int jacobi_rows(natrix_sim* s, int src, int depth, int r0, int r1, bool p_zero, 
     const Geom& g = s->g;
     if (s->pipeline == 0) {
         s->launches += launch_poisson_ref(s->p[src], s->div, s->obs, s->p[1 - src], g, r0, r1, st);
-    } else if (!jacobi_tb_supported(g)) {
-        // widths TMA cannot address (not a multiple of 16, or narrower than one strip)
-        s->launches += launch_poisson_mask(s->p[src], s->div, s->nbm, s->p[1 - src], g, r0, r1, st);
+    } else if (use_smem_kernel(s)) {
+        // small grids (latency-bound) and widths TMA cannot address: one tile per block in shared memory
+        const int n = launch_jacobi_smem(s->p[src], s->div, s->nbm, s->p[1 - src], g, depth, r0, r1, p_zero, s->sm_count, st);
+        if (n < 0) return fail(NATRIX_ERR_CUDA, std::string("k_jacobi_smem launch: ") + cudaGetErrorString(cudaGetLastError()));
+        s->launches += n;
     } else {
         int n = jacobi_tb_launch(s->tb, s->p[src], s->div, s->nbm, s->p[1 - src], g, depth, r0, r1, p_zero, s->packed,
                                  s->boxes.data(), (int)s->boxes.size() / 4, st);
@@ -409,14 +435,16 @@ int jacobi_rows(natrix_sim* s, int src, int depth, int r0, int r1, bool p_zero, 
     return 0;
 }
 
-int jacobi_launch_depth(const natrix_sim* s) {
-    return (s->pipeline == 0 || !jacobi_tb_supported(s->g)) ? 1 : s->jacobi_depth;
-}
-
 int phase_jacobi(natrix_sim* s, int sweeps) {
+    Range nvtx_range("natrix.jacobi");
     int left = sweeps;
     while (left > 0) {
-        const int t = std::min(left, jacobi_launch_depth(s));
+        int t = std::min(left, jacobi_launch_depth(s));
+        if (use_smem_kernel(s)) {
+            // the fewest launches the depth allows, sweeps spread evenly over them (50 = 13 + 13 + 12 + 12)
+            const int launches = (left + t - 1) / t;
+            t = (left + launches - 1) / launches;
+        }
         if (int rc = jacobi_rows(s, s->pr, t, s->ext_lo(left - t), s->ext_hi(left - t), s->p_is_zero, s->st)) return rc;
         s->pr = 1 - s->pr;
         left -= t;
@@ -465,6 +493,7 @@ int ensure_edge_stream(natrix_sim* s) {
 
 // phase 4: the interior of the group's first launch; the host queues the exchange on st_edge next
 int phase_jacobi_interior(natrix_sim* s, int sweeps) {
+    Range nvtx_range("natrix.jacobi.interior");
     const Geom& g = s->g;
     const bool up = g.y0 > 0, down = g.y0 + g.hl < g.hg;
     if (s->group_open) return fail(NATRIX_ERR_STATE, "a Jacobi group is open: call phase 5 first");
@@ -483,6 +512,7 @@ int phase_jacobi_interior(natrix_sim* s, int sweeps) {
 
 // phase 5: the exchange is queued on st_edge; the first launch's edge zones there, the rest of the group on main
 int phase_jacobi_edges(natrix_sim* s, int sweeps) {
+    Range nvtx_range("natrix.jacobi.edges");
     const Geom& g = s->g;
     const bool up = g.y0 > 0, down = g.y0 + g.hl < g.hg;
     if (s->group_open != sweeps) return fail(NATRIX_ERR_STATE, "phase 5 must follow phase 4 with the same sweeps");
@@ -508,6 +538,7 @@ int phase_jacobi_edges(natrix_sim* s, int sweeps) {
 }
 
 int phase_project(natrix_sim* s) {
+    Range nvtx_range("natrix.subtract_gradient");
     const Geom& g = s->g;
     stamp(s, ST_GRAD);
     if (s->pipeline == 0)
@@ -565,6 +596,7 @@ void halo_ptrs(char* row0, size_t row_bytes, int hl, int side, int rows, char** 
 // One NCCL group: `rows` halo rows of every listed field swapped with both neighbouring ranks, on stream st.
 // Point-to-point only - the path has no collective.
 int exchange_fields(natrix_sim* s, const int* fields, int nfields, int rows, cudaStream_t st) {
+    Range nvtx_range("natrix.halo_exchange");
     if (rows <= 0 || !s->comm) return 0;
     const Geom& g = s->g;
     if (rows > g.halo || rows > g.hl)
@@ -596,6 +628,7 @@ int exchange_fields(natrix_sim* s, const int* fields, int nfields, int rows, cud
 
 // the same for the rows of a dye field (its own geometry), on the simulator's stream
 int exchange_dye(natrix_dye* d, int rows) {
+    Range nvtx_range("natrix.halo_exchange.dye");
     natrix_sim* s = d->sim;
     if (rows <= 0 || !s->comm) return 0;
     const Geom& g = d->g;
@@ -759,6 +792,7 @@ int natrix_create_slab(int width, int global_height, int row0, int rows, int hal
         return fail(NATRIX_ERR_CUDA, msg);
     }
     s->tb = jacobi_tb_create();
+    s->smem_depth = jacobi_smem_max_depth();
     *out = s;
     return 0;
 }
@@ -825,6 +859,13 @@ int natrix_set_option(natrix_sim* s, int option, int value) {
     case NATRIX_OPT_TIMING: s->timing = value ? 1 : 0; return 0;
     case NATRIX_OPT_PACKED: s->packed = value ? 1 : 0; return 0;
     case NATRIX_OPT_WARM_START: s->warm_start = value ? 1 : 0; return 0;
+    case NATRIX_OPT_JACOBI_KERNEL:
+        NEED(value >= 0 && value <= 2, "jacobi kernel must be 0 (auto), 1 (TMA register streaming) or 2 (shared memory)");
+        NEED(value != 1 || jacobi_tb_supported(s->g), "the TMA kernel needs width % 16 == 0 and width >= 128");
+        s->jacobi_kernel = value; return 0;
+    case NATRIX_OPT_SMEM_DEPTH:
+        NEED(value >= 1 && value <= 16, "shared-memory jacobi depth out of range (1..16)");
+        s->smem_depth = value; return 0;
     default: return fail(NATRIX_ERR_ARG, "unknown option id");
     }
 }
@@ -837,6 +878,8 @@ int natrix_get_option(natrix_sim* s, int option, int* value) {
     case NATRIX_OPT_TIMING: *value = s->timing; return 0;
     case NATRIX_OPT_PACKED: *value = s->packed; return 0;
     case NATRIX_OPT_WARM_START: *value = s->warm_start; return 0;
+    case NATRIX_OPT_JACOBI_KERNEL: *value = s->pipeline == 0 ? 0 : (use_smem_kernel(s) ? 2 : 1); return 0;   // the one in use
+    case NATRIX_OPT_SMEM_DEPTH: *value = s->smem_depth; return 0;
     default: return fail(NATRIX_ERR_ARG, "unknown option id");
     }
 }
@@ -930,7 +973,7 @@ int natrix_halo_rows_needed(natrix_sim* s, int phase, float dt) {
         return (int)reach + 4;
     }
     case 1: return 0;                 // phase 0 already produced rows ext(4)
-    case 2: return s->jacobi_depth;   // per launch; a group of k launches between two exchanges needs k times that
+    case 2: return jacobi_launch_depth(s);   // per launch; a group of k launches between two exchanges needs k times that
     case 3: return 1;
     default: return fail(NATRIX_ERR_ARG, "phase must be 0..3");
     }
@@ -993,6 +1036,7 @@ int natrix_comm_stats(natrix_sim* s, unsigned long long* exchanges, unsigned lon
 }
 
 int natrix_step(natrix_sim* s, float dt) {
+    Range nvtx_range("natrix.step");
     NEED(s, "null simulator");
     if (int rc = select_device(s)) return rc;
     if (s->g.hl != s->g.hg) {
@@ -1073,6 +1117,7 @@ int natrix_copy_in(natrix_sim* s, int field, const void* host, size_t bytes) {
 }
 
 int natrix_field_stats(natrix_sim* s, int field, double* out4) {
+    Range nvtx_range("natrix.field_stats");
     NEED(s && out4, "null argument");
     NEED(field >= NATRIX_VELOCITY && field <= NATRIX_VORTICITY, "stats are defined for float fields");
     if (int rc = select_device(s)) return rc;
@@ -1153,6 +1198,7 @@ int natrix_dye_add(natrix_dye* d, float px, float py, float radius, float streng
 }
 
 int natrix_dye_step(natrix_dye* d, float dt, float speed, float dissipation) {
+    Range nvtx_range("natrix.dye_step");
     DYE_LIVE(d);
     natrix_sim* s = d->sim;
     if (int rc = select_device(s)) return rc;

@@ -292,6 +292,51 @@ __device__ __forceinline__ void row_step2_fast(float2 (&a)[T][2][2], const LaneA
     out[1] = nw1;
 }
 
+// The first 2 T input rows of a tile only fill the pipeline: level t produces its first row that anything will
+// ever read (row t of the tile's input window) at input row 2 t, so at input row i only levels 1 .. LV = i / 2 have
+// work to do.  This is row_step2_fast cut off after level LV < T: the newest row of level LV is parked in that
+// level's state instead of leaving the kernel.  (With every level running from row 0, as the other bodies do, the
+// T (T + 1) level-steps skipped here produce values no later step consumes: 9 % of a 85-row tile at T = 8.)
+template <int T, bool PZERO, int PAR, int LV>
+__device__ __forceinline__ void row_step2_fill(float2 (&a)[T][2][2], const LaneAddr& sa, int i, int lane) {
+    static_assert(LV < T, "the fill body stops below the last level");
+    constexpr unsigned FULL = 0xffffffffu;
+    const float2 quarter = make_float2(0.25f, 0.25f);
+    const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
+    float2 part[LV > 0 ? LV : 1][2];
+#pragma unroll
+    for (int t = 1; t <= LV; ++t) {
+        const float2(&old)[2] = a[t - 1][PAR];
+        const float2(&mid)[2] = a[t - 1][PAR ^ 1];
+        const float sl = bitsel(mid[0].x, __shfl_sync(FULL, mid[1].y, lane_l), sa.edge_l);
+        const float sr = bitsel(mid[1].y, __shfl_sync(FULL, mid[0].x, lane_r), sa.edge_r);
+        const float2 s0 = make_float2(sl + mid[0].y, mid[0].x + mid[1].x);
+        const float2 s1 = make_float2(mid[0].y + mid[1].y, mid[1].x + sr);
+        part[t - 1][0] = __fadd2_rn(s0, old[0]);
+        part[t - 1][1] = __fadd2_rn(s1, old[1]);
+    }
+    float2 nw0, nw1;
+    if (PZERO) {
+        nw0 = nw1 = make_float2(0.0f, 0.0f);
+    } else {
+        const float4 v = lds128(sa.p + (uint32_t)(i & (P_ROWS - 1)) * (SW * 4));
+        nw0 = make_float2(v.x, v.y);
+        nw1 = make_float2(v.z, v.w);
+    }
+#pragma unroll
+    for (int t = 1; t <= LV; ++t) {
+        const float4 dv = lds128(sa.d + (uint32_t)((i - t) & (D_ROWS - 1)) * (SW * 4));
+        const float2 r0 = __fmul2_rn(__fadd2_rn(__fadd2_rn(part[t - 1][0], nw0), neg2(make_float2(dv.x, dv.y))), quarter);
+        const float2 r1 = __fmul2_rn(__fadd2_rn(__fadd2_rn(part[t - 1][1], nw1), neg2(make_float2(dv.z, dv.w))), quarter);
+        a[t - 1][PAR][0] = nw0;
+        a[t - 1][PAR][1] = nw1;
+        nw0 = r0;
+        nw1 = r1;
+    }
+    a[LV][PAR][0] = nw0;
+    a[LV][PAR][1] = nw1;
+}
+
 // Rows deep inside an obstacle: every cell of the strip has all four neighbours blocked, in every row in
 // flight, so each level is ((C + C) + C) + C - b, * 0.25 of the cell itself (shader.Poisson.comp:32-37 with
 // all four substitutions): no neighbours, no shuffles, no selects.
@@ -426,6 +471,25 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
     };
     using I0 = std::integral_constant<int, 0>;
     using I1 = std::integral_constant<int, 1>;
+    // groups whose four rows all lie in the fill phase (input rows < 2 T): T / 2 of them
+    constexpr int FILL_GROUPS = PACKED ? T / 2 : 0;
+    auto fill_rows = [&](auto gc, int i0) {           // the four rows of fill group G = decltype(gc)::value
+        constexpr int G = decltype(gc)::value;
+        if constexpr (PACKED && G < FILL_GROUPS) {
+            row_step2_fill<T, PZERO, 0, (4 * G + 0) / 2>(a2, sa, i0, lane);
+            row_step2_fill<T, PZERO, 1, (4 * G + 1) / 2>(a2, sa, i0 + 1, lane);
+            row_step2_fill<T, PZERO, 0, (4 * G + 2) / 2>(a2, sa, i0 + 2, lane);
+            row_step2_fill<T, PZERO, 1, (4 * G + 3) / 2>(a2, sa, i0 + 3, lane);
+        }
+    };
+    auto fill_group = [&](int g, int i0) {
+        switch (g) {
+        case 0: fill_rows(std::integral_constant<int, 0>{}, i0); break;
+        case 1: fill_rows(std::integral_constant<int, 1>{}, i0); break;
+        case 2: fill_rows(std::integral_constant<int, 2>{}, i0); break;
+        default: fill_rows(std::integral_constant<int, 3>{}, i0); break;
+        }
+    };
 
     // One TMA group (4 rows) per iteration: wait for it, put the next group in flight, consume it.
     // The select-free body runs when no row in flight has a mask bit anywhere in the warp.
@@ -452,6 +516,10 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
             busy = ((busy << 1) | a2_) & BUSY_MASK; solid = ((solid << 1) | s2) & BUSY_MASK;
             one_row(I1{}, i0 + 3);
             busy = ((busy << 1) | a3) & BUSY_MASK; solid = ((solid << 1) | s3) & BUSY_MASK;
+        } else if (PACKED && g < FILL_GROUPS) {
+            // pipeline fill: input rows 4 g .. 4 g + 3 feed levels 1 .. (4 g + h) / 2 only
+            solid = 0u;
+            fill_group(g, i0);
         } else {
             solid = 0u;
 #pragma unroll 1

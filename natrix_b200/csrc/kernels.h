@@ -62,6 +62,12 @@ int launch_render_frame(const float* dye, const float4* lut, const float2* vel, 
 // ---- fused pipeline (fused.cu / jacobi_tb.cu) ----------------------------------------------------
 int launch_poisson_mask(const float* pin, const float* div, const uint8_t* nbmask, float* pout,
                         Geom g, int r0, int r1, cudaStream_t st);
+// `depth` (1..16) sweeps pin -> pout for rows [r0, r1), one tile per block in shared memory (jacobi_smem.cu): any
+// width, meant for small grids.  Same contract as jacobi_tb_launch; returns launches, or -1 on a launch error.
+int launch_jacobi_smem(const float* pin, const float* div, const uint8_t* nbmask, float* pout, Geom g, int depth,
+                       int r0, int r1, bool p_is_zero, int sm_count, cudaStream_t st);
+int jacobi_smem_max_depth();             // default sweeps per launch (NATRIX_SMEM_DEPTH, <= 16)
+size_t jacobi_smem_cell_limit();         // grids up to this many cells prefer the shared-memory kernel
 // over1: one device int per band of OVER_BAND allocated rows, set when some |v| > 1 is written there
 int launch_gradient_mask(const float2* vin, const float* p, const uint8_t* nbmask, float2* vout,
                          Geom g, int r0, int r1, int* over1, cudaStream_t st);

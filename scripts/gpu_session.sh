@@ -1,5 +1,5 @@
 set -u
-OUT=gpurun_out/r2j; mkdir -p $OUT
+OUT=gpurun_out/r2k; mkdir -p $OUT
 timeout 1200 python -m pytest tests -m gpu -q -x > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/pytest_gpu.log
 timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; tail -3 $OUT/bench.err
 python - $OUT/bench.json <<'PY'

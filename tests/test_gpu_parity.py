@@ -40,29 +40,40 @@ def _mg():
     return mod
 
 
-def _sim_cls(pipeline, depth=None):
+TB, SMEM = 1, 2          # NATRIX_OPT_JACOBI_KERNEL: the TMA register-streaming kernel / the shared-memory kernel
+# (pipeline, Jacobi kernel): the reference-order pipeline, and the fused pipeline with each of its two Jacobi kernels
+# forced - small grids would otherwise only ever reach the shared-memory one
+PIPELINES = [(0, None), (1, TB), (1, SMEM)]
+
+
+def _sim_cls(pipeline, depth=None, kernel=None):
     def make(w, h, layout=None, **kw):
         s = FluidSimulator(w, h, layout, **kw)
         s.set_option(L.OPT_PIPELINE, pipeline)
+        if kernel == TB and (w % 16 or w < 128):
+            pass                                   # TMA cannot address this width: the library's own choice
+        elif kernel is not None:
+            s.set_option(L.OPT_JACOBI_KERNEL, kernel)
+            assert s.get_option(L.OPT_JACOBI_KERNEL) == (kernel if pipeline else 0)
         if depth is not None:
-            s.set_option(L.OPT_JACOBI_DEPTH, depth)
+            s.set_option(L.OPT_SMEM_DEPTH if kernel == SMEM else L.OPT_JACOBI_DEPTH, depth)
         return s
     return make
 
 
-@pytest.mark.parametrize("pipeline", [0, 1])
-def test_small_case_matches_golden_fixture(pipeline, golden_dir):
+@pytest.mark.parametrize("pipeline,kernel", PIPELINES)
+def test_small_case_matches_golden_fixture(pipeline, kernel, golden_dir):
     want = np.load(golden_dir / "small_case.npz")
-    got = _mg().small_case(_sim_cls(pipeline), SmoothParticlesArea)
-    assert_fields_close(got, {k: want[k] for k in want.files}, f"pipeline {pipeline}: ", exact=True)
+    got = _mg().small_case(_sim_cls(pipeline, kernel=kernel), SmoothParticlesArea)
+    assert_fields_close(got, {k: want[k] for k in want.files}, f"pipeline {pipeline} kernel {kernel}: ", exact=True)
 
 
-@pytest.mark.parametrize("pipeline", [0, 1])
-def test_config1_demo_ten_steps_vs_numpy_oracle(pipeline):
+@pytest.mark.parametrize("pipeline,kernel", PIPELINES)
+def test_config1_demo_ten_steps_vs_numpy_oracle(pipeline, kernel):
     """config 1: demo grid 640x360 + dye 1280x720, random initial velocity, 10 frames."""
     w = W.demo_workload()
     w.init = "random"
-    gsim, gdye = W.build(w, _sim_cls(pipeline), SmoothParticlesArea)
+    gsim, gdye = W.build(w, _sim_cls(pipeline, kernel=kernel), SmoothParticlesArea)
     osim, odye = W.build(w, OracleFluidSimulator, OracleSmoothParticlesArea)
     for k in range(10):
         W.run_step(w, gsim, gdye, k)
@@ -82,11 +93,11 @@ def test_config1_zero_state_first_frame_dt0():
         assert_fields_close(W.fields_of(gsim, gdye), W.fields_of(osim, odye), f"frame {k}: ", exact=True)
 
 
-@pytest.mark.parametrize("pipeline", [0, 1])
-def test_config2_1024_twenty_steps_vs_c_oracle(pipeline):
+@pytest.mark.parametrize("pipeline,kernel", PIPELINES)
+def test_config2_1024_twenty_steps_vs_c_oracle(pipeline, kernel):
     """config 2: 1024^2, 50 iterations, vorticity confinement, 4 circular obstacles."""
     w = W.cfg2_workload()
-    gsim, _ = W.build(w, _sim_cls(pipeline), None)
+    gsim, _ = W.build(w, _sim_cls(pipeline, kernel=kernel), None)
     osim, _ = W.build(w, COracleFluidSimulator, None)
     for k in range(20):
         W.run_step(w, gsim, None, k)
@@ -95,16 +106,16 @@ def test_config2_1024_twenty_steps_vs_c_oracle(pipeline):
             assert_fields_close(W.fields_of(gsim), W.fields_of(osim), f"step {k}: ", exact=True)
 
 
-@pytest.mark.parametrize("depth", [1, 2, 3, 4, 5, 6, 7, 8])
-def test_temporal_blocking_is_depth_independent(depth):
-    """T sweeps per launch must equal T launches of one sweep, bit for bit, for every T,
-    including the remainder block (iterations = 19 is not a multiple of any T > 1)."""
+@pytest.mark.parametrize("kernel,depth", [(TB, d) for d in range(1, 9)] + [(SMEM, d) for d in (1, 2, 5, 8, 11, 13, 16)])
+def test_temporal_blocking_is_depth_independent(kernel, depth):
+    """T sweeps per launch must equal T launches of one sweep, bit for bit, for every T and for both temporally
+    blocked kernels, including the remainder block (iterations = 19 is not a multiple of any T > 1)."""
     w, h = 640, 296
     rng = np.random.default_rng(depth)
     v0 = (0.6 * rng.uniform(-1, 1, (h, w, 2))).astype(np.float32)
     out = []
     for pipeline, d in ((0, None), (1, depth)):
-        s = _sim_cls(pipeline, d)(w, h)
+        s = _sim_cls(pipeline, d, kernel if pipeline else None)(w, h)
         s.vorticity, s.viscosity, s.iterations = 0.7, 0.2, 19
         s.upload("velocity", v0)
         for _ in range(2):
@@ -122,8 +133,10 @@ def test_temporal_blocking_is_depth_independent(depth):
 def test_ragged_and_degenerate_sizes_vs_oracle(w, h):
     rng = np.random.default_rng(w + 1000 * h)
     v0 = rng.uniform(-1.5, 1.5, (h, w, 2)).astype(np.float32)   # |v| > 1: back-traces leave the grid
-    for pipeline in (0, 1):
-        g = _sim_cls(pipeline)(w, h)
+    for pipeline, kernel in PIPELINES:
+        if kernel == TB and (w % 16 or w < 128):
+            continue                                # the same run as (1, SMEM): TMA cannot address this width
+        g = _sim_cls(pipeline, kernel=kernel)(w, h)
         o = OracleFluidSimulator(w, h)
         for s in (g, o):
             s.vorticity, s.viscosity, s.iterations, s.speed = 2.0, 0.3, 11, 300.0
@@ -321,7 +334,7 @@ def test_results_do_not_depend_on_scheduling_hints(monkeypatch):
     for env in ({}, {"NATRIX_TB_CHUNK": "20"}, {"NATRIX_TB_KAPPA": "3.5", "NATRIX_TB_SHAPE": "0"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
-        s = FluidSimulator(w, h)
+        s = _sim_cls(1, kernel=TB)(w, h)
         s.vorticity, s.viscosity, s.iterations = 1.0, 0.0, 21
         s.upload("velocity", v0)
         for _ in range(2):
@@ -401,7 +414,7 @@ def test_moving_obstacles_every_step_a_new_tile_plan_vs_oracle():
     import dataclasses
     w = W.Workload("moving-512x256", 512, 256, 17, 1.0, 0.1, circles=[(0.2, 0.3, 18.0), (0.6, 0.7, 30.0), (0.9, 0.5, 12.0)],
                    splats_per_step=1, splat_radius=20.0, init="random", drift=5.0)
-    g, _ = W.build(w, _sim_cls(1), None)
+    g, _ = W.build(w, _sim_cls(1, kernel=TB), None)
     o, _ = W.build(w, OracleFluidSimulator, None)
     for k in range(40):
         W.run_step(w, g, None, k)
@@ -411,7 +424,7 @@ def test_moving_obstacles_every_step_a_new_tile_plan_vs_oracle():
     hits, misses = g.plan_cache_stats()
     assert misses >= 40 and hits >= 40, (hits, misses)          # a new plan per step, reused by the step's later launches
     static = dataclasses.replace(w, drift=0.0)
-    g2, _ = W.build(static, _sim_cls(1), None)
+    g2, _ = W.build(static, _sim_cls(1, kernel=TB), None)
     for k in range(5):
         W.run_step(static, g2, None, k)
     assert g2.plan_cache_stats()[1] <= 4                        # the same circles every step: the plans are found again
@@ -426,16 +439,16 @@ def test_headless_demo_writes_frames(tmp_path):
     assert all(p.stat().st_size > 2000 for p in written)
 
 
-@pytest.mark.parametrize("pipeline", [0, 1])
-def test_warm_start_option_vs_oracle(pipeline):
+@pytest.mark.parametrize("pipeline,kernel", PIPELINES)
+def test_warm_start_option_vs_oracle(pipeline, kernel):
     """NATRIX_OPT_WARM_START (not reference behaviour): the pressure of the previous step is the
     initial guess; still bit-identical to the oracle run with the pressure clear skipped, and different from the
     reference-order run."""
     w = W.cfg2_workload()
     w.width, w.height, w.iterations = 384, 256, 21
-    g, _ = W.build(w, _sim_cls(pipeline), None)
+    g, _ = W.build(w, _sim_cls(pipeline, kernel=kernel), None)
     o, _ = W.build(w, OracleFluidSimulator, None)
-    cold, _ = W.build(w, _sim_cls(pipeline), None)
+    cold, _ = W.build(w, _sim_cls(pipeline, kernel=kernel), None)
     g.warm_start = True
     o.warm_start = True
     assert g.warm_start and not cold.warm_start
@@ -509,9 +522,9 @@ def test_pure_c_host_matches_the_python_mirror():
         assert got[name] == list(want[name]), f"{name}: C host {got[name]} != mirror {list(want[name])}"
 
 
-@pytest.mark.parametrize("pipeline", [0, 1])
+@pytest.mark.parametrize("pipeline,kernel", PIPELINES)
 @pytest.mark.parametrize("seed", range(20))
-def test_random_scenarios_vs_c_oracle(seed, pipeline):
+def test_random_scenarios_vs_c_oracle(seed, pipeline, kernel):
     """Differential test on seeded random scripts of public-API calls (workloads.random_scenario): ragged and
     1-cell-wide grids, every parameter corner, obstacles partly outside the grid, zero radii, dt = 0, dye grids of
     unrelated size - every field of every frame bit-identical to the C oracle."""
@@ -523,4 +536,4 @@ def test_random_scenarios_vs_c_oracle(seed, pipeline):
     def check(k, s, d):
         assert_fields_close(W.fields_of(s, d), frames[k], f"seed {seed} {scn['size']} frame {k}: ", exact=True)
 
-    W.play_scenario(scn, _sim_cls(pipeline), SmoothParticlesArea, check)
+    W.play_scenario(scn, _sim_cls(pipeline, kernel=kernel), SmoothParticlesArea, check)
