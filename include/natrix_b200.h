@@ -53,7 +53,11 @@ enum natrix_field {
     NATRIX_DIVERGENCE = 2,
     NATRIX_VORTICITY = 3,
     NATRIX_OBSTACLES = 4,
-    NATRIX_NBMASK = 5        /* internal 4-bit blocked-neighbour mask, 1 byte per cell */
+    NATRIX_NBMASK = 5,       /* internal blocked-neighbour mask, 1 byte per cell: bits 0-3 = L/R/B/T neighbour is solid
+                                or outside the grid, bit 4 = the cell's scaled divergence holds b itself (see DIV4) */
+    NATRIX_DIV4 = 6          /* internal: 0.25 * divergence, the copy the Jacobi sweeps read (the sweep then ends in one
+                                fused multiply-add, bit-identical to the shader's (sum - b) * 0.25); the field a slab
+                                exchanges with its neighbours before the first sweep */
 };
 
 enum natrix_option {

@@ -11,13 +11,14 @@ import subprocess
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libnatrix_b200.so"
+# NATRIX_B200_LIB: another build of the same library (A/B timing of kernel variants, scripts/ab_build.sh)
+LIB_PATH = Path(os.environ.get("NATRIX_B200_LIB") or _PKG / "libnatrix_b200.so")
 
 # enum natrix_field / natrix_option (include/natrix_b200.h)
-VELOCITY, PRESSURE, DIVERGENCE, VORTICITY, OBSTACLES, NBMASK = range(6)
+VELOCITY, PRESSURE, DIVERGENCE, VORTICITY, OBSTACLES, NBMASK, DIV4 = range(7)
 OPT_PIPELINE, OPT_JACOBI_DEPTH, OPT_TIMING, OPT_WARM_START, OPT_PACKED, OPT_JACOBI_KERNEL, OPT_SMEM_DEPTH = range(7)
 
-FIELD_COMPONENTS = {VELOCITY: 2, PRESSURE: 1, DIVERGENCE: 1, VORTICITY: 1, OBSTACLES: 2, NBMASK: 1}
+FIELD_COMPONENTS = {VELOCITY: 2, PRESSURE: 1, DIVERGENCE: 1, VORTICITY: 1, OBSTACLES: 2, NBMASK: 1, DIV4: 1}
 
 # every symbol include/natrix_b200.h declares: name -> (restype, argtypes)
 _vp, _f, _i, _d, _sz = C.c_void_p, C.c_float, C.c_int, C.c_double, C.c_size_t

@@ -27,6 +27,7 @@ _FIELD_IDS = {
     "vorticity": L.VORTICITY,
     "obstacles": L.OBSTACLES,
     "nbmask": L.NBMASK,
+    "div4": L.DIV4,          # internal: 0.25 * divergence, the copy the Jacobi sweeps read
 }
 
 

@@ -100,11 +100,12 @@ struct natrix_sim {
     // allocations (base) and row-0 views
     float2* vel_base[2] = {nullptr, nullptr};
     float* p_base[2] = {nullptr, nullptr};
-    float *div_base = nullptr, *vort_base = nullptr;
+    float *div_base = nullptr, *vort_base = nullptr, *div4_base = nullptr;
     uint8_t *obs_base = nullptr, *nbm_base = nullptr;
     float2* vel[2] = {nullptr, nullptr};
     float* p[2] = {nullptr, nullptr};
     float *div = nullptr, *vort = nullptr;
+    float* div4 = nullptr;                       // 0.25 * div, what the temporally blocked Jacobi kernels read (common.cuh NB_RAW)
     uint8_t *obs = nullptr, *nbm = nullptr;
     int vr = 0, pr = 0;                          // VELOCITY_READ / PRESSURE_READ indices
     // parameters (fluid_simulator.py:28-35 defaults)
@@ -347,7 +348,7 @@ int phase_advect(natrix_sim* s, float dt) {
         // velocity buffer flips once (the intermediate velocities never reach memory)
         if (s->has_borders)
             s->launches += launch_zero_borders(s->vel[s->vr], g, s->ext_lo(g.halo), s->ext_hi(g.halo), s->st);
-        s->launches += launch_preproject(s->vel[s->vr], s->obs, s->vel[1 - s->vr], s->vort, s->div, s->nbm, gv, 0, g.hl,
+        s->launches += launch_preproject(s->vel[s->vr], s->obs, s->vel[1 - s->vr], s->vort, s->div, s->div4, s->nbm, gv, 0, g.hl,
                                          dt, s->speed, s->dissipation, s->vorticity, s->viscous != 0, s->alpha,
                                          s->rbeta, s->sm_count, s->d_err, s->st);
         s->vr = 1 - s->vr;
@@ -385,7 +386,7 @@ int phase_forces(natrix_sim* s, float dt) {
         s->vr = 1 - s->vr;
     }
     stamp(s, ST_DIV);
-    s->launches += launch_divergence(s->vel[s->vr], s->obs, s->div, s->nbm, g, 0, g.hl, s->st);
+    s->launches += launch_divergence(s->vel[s->vr], s->obs, s->div, s->div4, s->nbm, g, 0, g.hl, s->st);
     // clear pressure (fluid_simulator.py:236-248); halo rows included so the first Jacobi
     // block needs no exchange
     if (!s->warm_start) {
@@ -423,11 +424,11 @@ int jacobi_rows(natrix_sim* s, int src, int depth, int r0, int r1, bool p_zero, 
         s->launches += launch_poisson_ref(s->p[src], s->div, s->obs, s->p[1 - src], g, r0, r1, st);
     } else if (use_smem_kernel(s)) {
         // small grids (latency-bound) and widths TMA cannot address: one tile per block in shared memory
-        const int n = launch_jacobi_smem(s->p[src], s->div, s->nbm, s->p[1 - src], g, depth, r0, r1, p_zero, s->sm_count, st);
+        const int n = launch_jacobi_smem(s->p[src], s->div4, s->nbm, s->p[1 - src], g, depth, r0, r1, p_zero, s->sm_count, st);
         if (n < 0) return fail(NATRIX_ERR_CUDA, std::string("k_jacobi_smem launch: ") + cudaGetErrorString(cudaGetLastError()));
         s->launches += n;
     } else {
-        int n = jacobi_tb_launch(s->tb, s->p[src], s->div, s->nbm, s->p[1 - src], g, depth, r0, r1, p_zero, s->packed,
+        int n = jacobi_tb_launch(s->tb, s->p[src], s->div4, s->nbm, s->p[1 - src], g, depth, r0, r1, p_zero, s->packed,
                                  s->boxes.data(), (int)s->boxes.size() / 4, st);
         if (n < 0) return fail(NATRIX_ERR_CUDA, std::string("jacobi_tb: ") + jacobi_tb_error(s->tb));
         s->launches += n;
@@ -577,6 +578,7 @@ int field_info(natrix_sim* s, int field, void** base_row0, size_t* elem) {
     case NATRIX_VORTICITY: *base_row0 = s->vort; *elem = sizeof(float); return 0;
     case NATRIX_OBSTACLES: *base_row0 = s->obs; *elem = sizeof(uint8_t); return 0;
     case NATRIX_NBMASK: *base_row0 = s->nbm; *elem = sizeof(uint8_t); return 0;
+    case NATRIX_DIV4: *base_row0 = s->div4; *elem = sizeof(float); return 0;
     default: return fail(NATRIX_ERR_ARG, "unknown field id");
     }
 }
@@ -700,7 +702,7 @@ int step_slab(natrix_sim* s, float dt) {
         }
         if (i == 0) {
             // p starts at zero, halos included - unless the simulator warm-starts from the last step's pressure
-            const int first[3] = {NATRIX_DIVERGENCE, NATRIX_NBMASK, NATRIX_PRESSURE};
+            const int first[3] = {NATRIX_DIV4, NATRIX_NBMASK, NATRIX_PRESSURE};      // the sweeps read the scaled divergence
             if (int rc = exchange_fields(s, first, s->warm_start ? 3 : 2, std::min(span, n), xs)) return rc;
         } else {
             if (int rc = exchange_fields(s, &prs, 1, t, xs)) return rc;
@@ -773,6 +775,7 @@ int natrix_create_slab(int width, int global_height, int row0, int rows, int hal
     }
     if (e == cudaSuccess) e = alloc_rows(&s->div_base, &s->div, s);
     if (e == cudaSuccess) e = alloc_rows(&s->vort_base, &s->vort, s);
+    if (e == cudaSuccess) e = alloc_rows(&s->div4_base, &s->div4, s);
     if (e == cudaSuccess) e = alloc_rows(&s->obs_base, &s->obs, s);
     if (e == cudaSuccess) e = alloc_rows(&s->nbm_base, &s->nbm, s);
     s->nbands = (int)((s->rows_alloc + OVER_BAND - 1) / OVER_BAND);
@@ -809,7 +812,7 @@ int natrix_destroy(natrix_sim* s) {
     if (s->comm) { nccl()->CommDestroy(s->comm); s->comm = nullptr; }
     jacobi_tb_destroy(s->tb);
     for (int i = 0; i < 2; ++i) { cudaFree(s->vel_base[i]); cudaFree(s->p_base[i]); }
-    cudaFree(s->div_base); cudaFree(s->vort_base); cudaFree(s->obs_base); cudaFree(s->nbm_base);
+    cudaFree(s->div_base); cudaFree(s->vort_base); cudaFree(s->div4_base); cudaFree(s->obs_base); cudaFree(s->nbm_base);
     cudaFree(s->d_err); cudaFree(s->d_scratch); cudaFree(s->d_out4); cudaFree(s->d_tmp2);
     if (s->h_err) cudaFreeHost(s->h_err);
     if (s->err_event) cudaEventDestroy(s->err_event);
@@ -1110,6 +1113,8 @@ int natrix_copy_in(natrix_sim* s, int field, const void* host, size_t bytes) {
     }
     NEED(bytes == n * elem, "copy_in size does not match the field");
     CU(cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, s->st));
+    if (field == NATRIX_DIVERGENCE || field == NATRIX_NBMASK)    // keep the scaled copy and its NB_RAW bits in step
+        s->launches += launch_rescale_divergence(s->div, s->div4, s->nbm, n, s->st);
     CU(cudaStreamSynchronize(s->st));
     if (field == NATRIX_PRESSURE) s->p_is_zero = false;
     if (field == NATRIX_VELOCITY) CU(cudaMemsetAsync(s->d_err + 1, 1, s->nbands * sizeof(int), s->st));   // unknown range
@@ -1119,7 +1124,7 @@ int natrix_copy_in(natrix_sim* s, int field, const void* host, size_t bytes) {
 int natrix_field_stats(natrix_sim* s, int field, double* out4) {
     Range nvtx_range("natrix.field_stats");
     NEED(s && out4, "null argument");
-    NEED(field >= NATRIX_VELOCITY && field <= NATRIX_VORTICITY, "stats are defined for float fields");
+    NEED((field >= NATRIX_VELOCITY && field <= NATRIX_VORTICITY) || field == NATRIX_DIV4, "stats are defined for float fields");
     if (int rc = select_device(s)) return rc;
     if (field == NATRIX_VELOCITY)
         if (int rc = flush_splats(s)) return rc;

@@ -34,7 +34,22 @@ enum : uint8_t { OBS_FREE = 0, OBS_DYNAMIC = 1 /* (1,0) */, OBS_STATIC = 2 /* (0
 // bits of the blocked-neighbour mask consumed by the Jacobi and gradient kernels:
 // set when that neighbour is solid OR lies outside the global domain; in both cases
 // shader.Poisson.comp:32-35 / shader.SubtractGradient.comp:35-42 use the centre pressure.
-enum : uint8_t { NB_L = 1, NB_R = 2, NB_B = 4, NB_T = 8 };
+enum : uint8_t { NB_L = 1, NB_R = 2, NB_B = 4, NB_T = 8,
+                 // The Jacobi kernels read the divergence PRE-SCALED: b4 = 0.25 * b, so that a sweep ends in ONE fused
+                 // multiply-add, fma(sum, 0.25, -b4), instead of the shader's subtract-then-scale.  The two are bit-identical
+                 // whenever 0.25 * b is exact (proof and brute-force check in DESIGN.md 5.1: scaling by a power of two
+                 // commutes with rounding, and where the scaled result is subnormal the shader's first rounding is either
+                 // exact or a tie that rounds to the same multiple of four).  0.25 * b is inexact only for a non-zero
+                 // |b| < 2^-124 whose last two mantissa bits are not both zero; such a cell stores b itself in the scaled
+                 // field and carries this bit, which sends its row to the select body, where the shader's two-step form is used.
+                 NB_RAW = 16 };
+
+// the scaled divergence the Jacobi kernels read, and whether the cell has to take the unfused form (see NB_RAW)
+__device__ __forceinline__ float scaled_divergence(float b, bool* raw) {
+    const float b4 = b * 0.25f;
+    *raw = b4 * 4.0f != b;
+    return *raw ? b : b4;
+}
 
 __host__ __device__ __forceinline__ int clampi(int v, int lo, int hi) {
     return v < lo ? lo : (v > hi ? hi : v);

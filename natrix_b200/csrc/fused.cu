@@ -3,13 +3,15 @@
 //  * k_preproject: ONE pass for everything the reference does between the start of update() and the
 //    Poisson loop - [InitBoundaries] -> AdvectVelocity -> CalcVorticity -> ApplyVorticity ->
 //    [Viscosity] -> Divergence (+ the blocked-neighbour mask).  Reads velocity 8 B + obstacles 1 B per
-//    cell, writes velocity 8 B, vorticity 4 B, divergence 4 B, mask 1 B = 26 B/cell, instead of
+//    cell, writes velocity 8 B, vorticity 4 B, divergence 4 B, scaled divergence 4 B, mask 1 B = 30 B/cell, instead of
 //    92 B/cell (108 with viscosity) for the five dispatches.
 //  * impulse kernels that touch only the bounding boxes of the splats, in place;
 //  * the gradient subtraction driven by the mask.
 //
 // All of them produce bit-identical results to the one-kernel-per-shader versions in
 // stages_ref.cu (same expressions, same operand order, -fmad=false).
+#include <type_traits>
+
 #include "kernels.h"
 
 namespace natrix {
@@ -24,7 +26,6 @@ namespace {
 // 3-row windows held in registers; left/right neighbours come from the adjacent lanes by shuffle.
 constexpr int PSW = 128;      // strip width
 constexpr int PHX = 4;        // halo columns per side = number of x-neighbour stages
-constexpr int PWARPS = 8;
 
 struct PreParams {
     int r0, r1;               // output rows (local)
@@ -41,52 +42,48 @@ __device__ __forceinline__ void copy4(float (&d)[4], const float (&s)[4]) {
     for (int j = 0; j < 4; ++j) d[j] = s[j];
 }
 
-// Bilinear back-trace of one cell (ref: shader.AdvectVelocity.comp:36-49; same expressions as
-// common.cuh advect_cell) with the two gathered rows addressed through row pointers.  SLAB adds the
-// check that the gathered rows are rows this slab holds.
-template <bool SLAB>
-__device__ __forceinline__ float2 advect_gather(const float2* __restrict__ vin, const Geom& g, int x, int gy, float2 vel,
-                                                float dt, float speed, float diss, int* __restrict__ err) {
-    const float fx = (float)x - vel.x * dt * speed;
-    const float fy = (float)gy - vel.y * dt * speed;
-    Corners c = corners(fx, fy, g.w, g.hg);
-    if (SLAB) {
-        const int lo = g.y0 - g.halo, hi = g.y0 + g.hl + g.halo - 1;
-        if (c.by < lo || c.ty > hi) *err = 1;
-        c.by = clampi(c.by, lo, hi);
-        c.ty = clampi(c.ty, lo, hi);
-    }
-    const float2* rb_ = vin + (ptrdiff_t)(c.by - g.y0) * g.w;
-    const float2* rt_ = rb_ + (c.ty - c.by) * g.w;
-    const float2 lt = rt_[c.bx], rt = rt_[c.tx], lb = rb_[c.bx], rb = rb_[c.tx];
-    const float h1x = mixf(lt.x, rt.x, c.dx), h1y = mixf(lt.y, rt.y, c.dx);
-    const float h2x = mixf(lb.x, rb.x, c.dx), h2y = mixf(lb.y, rb.y, c.dx);
-    float2 o;
-    o.x = clampf(mixf(h2x, h1x, c.dy) * diss, -1.0f, 1.0f);
-    o.y = clampf(mixf(h2y, h1y, c.dy) * diss, -1.0f, 1.0f);
-    return o;
+// Clamped floor / ceil corners of a back-traced position with the UNclamped delta (ref:
+// shader.AdvectVelocity.comp:38-42), in integers: int(clamp(floor(f), 0, m)) == clamp(int_floor(f), 0, m)
+// for every float f - cvt.rmi / cvt.rpi saturate where the float clamp would have cut anyway, and NaN gives 0
+// both ways - so this is common.cuh corners() with 4 conversions and 4 integer clamps (VIMNMX.RELU) instead of
+// 4 roundings, 8 float min / max and 4 conversions.
+__device__ __forceinline__ Corners corners_int(float fx, float fy, int w, int h) {
+    Corners c;
+    c.bx = __vimin_s32_relu(__float2int_rd(fx), w - 1);      // max(min(v, w - 1), 0) in one instruction
+    c.tx = __vimin_s32_relu(__float2int_ru(fx), w - 1);
+    c.by = __vimin_s32_relu(__float2int_rd(fy), h - 1);
+    c.ty = __vimin_s32_relu(__float2int_ru(fy), h - 1);
+    c.dx = fx - (float)c.bx;
+    c.dy = fy - (float)c.by;
+    return c;
 }
 
-// The same back-trace in two halves, so that the four gathers of a cell can be in flight across a whole row
-// of arithmetic (PIPE variant of k_preproject): issue = corners, addresses, loads; finish = the three mixes.
+// The bilinear back-trace of one cell (ref: shader.AdvectVelocity.comp:36-49; same expressions as common.cuh
+// advect_cell) in two halves, so that the four gathers of a cell can be in flight across a whole row of
+// arithmetic: issue = corners, addresses, loads; finish = the three mixes.  SLAB adds the check that the gathered
+// rows are rows this slab holds.
 struct Gather { float2 lt, rt, lb, rb; float dx, dy; };
 template <bool SLAB>
-__device__ __forceinline__ void gather_issue(Gather& q, const float2* __restrict__ vin, const Geom& g, int x, int gy,
-                                             float2 vel, float dt, float speed, int* __restrict__ err) {
-    const float fx = (float)x - vel.x * dt * speed;
-    const float fy = (float)gy - vel.y * dt * speed;
-    Corners c = corners(fx, fy, g.w, g.hg);
+__device__ __forceinline__ void gather_issue(Gather& q, const float2* __restrict__ rowp, const Geom& g, float fxc, int gy,
+                                             int gyw, float fyc, float2 vel, float dt, float speed, int* __restrict__ err) {
+    const float fx = fxc - vel.x * dt * speed;          // fxc = (float)x, fyc = (float)gy
+    const float fy = fyc - vel.y * dt * speed;
+    Corners c = corners_int(fx, fy, g.w, g.hg);
     if (SLAB) {
         const int lo = g.y0 - g.halo, hi = g.y0 + g.hl + g.halo - 1;
         if (c.by < lo || c.ty > hi) *err = 1;
         c.by = clampi(c.by, lo, hi);
         c.ty = clampi(c.ty, lo, hi);
     }
-    const float2* rb_ = vin + (ptrdiff_t)(c.by - g.y0) * g.w;
-    const float2* rt_ = rb_ + (c.ty - c.by) * g.w;
-    q.lt = rt_[c.bx]; q.rt = rt_[c.tx]; q.lb = rb_[c.bx]; q.rb = rb_[c.tx];
+    // 32-bit cell offsets from the first cell of the row the warp is on (rowp; gyw = gy * width): one multiply-add
+    // per gathered row, one add and one 64-bit multiply-add per load (launch_preproject checks the grid has < 2^31 cells)
+    const int ob = c.by * g.w - gyw, ot = c.ty * g.w - gyw;
+    q.lt = __ldg(rowp + (ot + c.bx)); q.rt = __ldg(rowp + (ot + c.tx));      // ld.global.nc, as the compiler
+    q.lb = __ldg(rowp + (ob + c.bx)); q.rb = __ldg(rowp + (ob + c.tx));      // infers for a plain __restrict__ read
     q.dx = c.dx; q.dy = c.dy;
 }
+// (The three mixes are scalar on purpose: written with the 2-wide fp32 intrinsics, ptxas 12.9 contracts
+// mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false, which rounds once where the shader rounds twice.)
 __device__ __forceinline__ float2 gather_finish(const Gather& q, float diss) {
     const float h1x = mixf(q.lt.x, q.rt.x, q.dx), h1y = mixf(q.lt.y, q.rt.y, q.dx);
     const float h2x = mixf(q.lb.x, q.rb.x, q.dx), h2y = mixf(q.lb.y, q.rb.y, q.dx);
@@ -99,13 +96,14 @@ __device__ __forceinline__ float2 gather_finish(const Gather& q, float diss) {
 // InitBoundaries (shader.InitBoundaries.comp:14-34) is NOT folded in here: when has_borders is set the
 // border lines of the READ buffer are zeroed in place by k_zero_borders first, exactly like the
 // reference's dispatch does (2 (W + H) cells; cheaper than testing every gathered corner).
-// PIPE = false: 8 warps x 2 CTAs per SM, the gathers of a row are consumed in the same iteration.
-// PIPE = true : 12 warps x 1 CTA per SM (168 registers); the gathers of row ly+1 are issued before the
-//               vorticity / confinement / divergence arithmetic of row ly and consumed one iteration later.
+// Both variants run 12 warps x 1 CTA per SM (up to 168 registers).
+// PIPE = false: the gathers of a row are consumed in the same iteration (small grids: shorter warm-up per tile).
+// PIPE = true : the gathers of row ly+1 are issued before the vorticity / confinement / divergence arithmetic
+//               of row ly and consumed one iteration later; the rolling windows rotate without register moves.
 template <bool VISCOUS, bool SLAB, bool PIPE>
-__global__ void __launch_bounds__(PIPE ? 384 : 256, PIPE ? 1 : 2)
+__global__ void __launch_bounds__(384, 1)
 k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, float2* __restrict__ vout,
-             float* __restrict__ vort, float* __restrict__ div, uint8_t* __restrict__ nbmask, const Geom g,
+             float* __restrict__ vort, float* __restrict__ div, float* __restrict__ div4, uint8_t* __restrict__ nbmask, const Geom g,
              const PreParams prm, int* __restrict__ err) {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int DEPTH = VISCOUS ? 4 : 3;            // rows between the advected row and the divergence row
@@ -123,13 +121,19 @@ k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, fl
     const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
     const int xc0 = clampi(xa, 0, g.w - 4);            // clamped column group for memory safety (halo lanes)
 
-    float2 A0[4], A1[4], B0[4], B1[4], C0[4], C1[4];   // older / newer kept rows of each stage
-    float W0[4], W1[4];
+    // Rolling windows: three rows per stage - older, middle, newest - in three register slots whose roles rotate
+    // from one row to the next.  The row loop is unrolled three times so that every slot index is a compile-time
+    // constant: no register ever moves (the earlier two-slot version spent a tenth of its instructions on moves).
+    float2 A[3][4], B[3][4], C[3][4];                  // advected / confined / viscous velocity
+    float Wv[3][4];                                    // vorticity
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        A0[j] = A1[j] = B0[j] = B1[j] = C0[j] = C1[j] = make_float2(0.0f, 0.0f);
-        W0[j] = W1[j] = 0.0f;
-    }
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            A[k][j] = B[k][j] = C[k][j] = make_float2(0.0f, 0.0f);
+            Wv[k][j] = 0.0f;
+        }
+    const float fxc[4] = {(float)xc0, (float)(xc0 + 1), (float)(xc0 + 2), (float)(xc0 + 3)};
 
     // The centre cells of a row (obstacle word + 4 velocities) are the only loads that miss to DRAM - the
     // back-trace gathers land on rows this warp has just streamed through.  They are fetched one row ahead
@@ -147,7 +151,7 @@ k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, fl
     };
     fetch_row(out_lo - DEPTH);
 
-    // PIPE: gathers in flight for the row about to be advected
+    // gathers in flight for the row about to be advected (PIPE: issued one row ahead of their use)
     Gather G[4];
     uint32_t g_ow = 0u;
     bool g_valid = false;
@@ -160,47 +164,45 @@ k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, fl
         if (g_valid) {
             const float2 cv[4] = {make_float2(c01.x, c01.y), make_float2(c01.z, c01.w), make_float2(c23.x, c23.y),
                                   make_float2(c23.z, c23.w)};
+            const float fyc = (float)gy_;
+            const float2* rowp = vin + (ptrdiff_t)ly_ * g.w;
+            asm volatile("" : "+l"(rowp));           // keep the row pointer a value of its own (else it is re-derived per load)
+            const int gyw = gy_ * g.w;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) gather_issue<SLAB>(G[j], vin, g, xc0 + j, gy_, cv[j], prm.dt, prm.speed, err);
+            for (int j = 0; j < 4; ++j) gather_issue<SLAB>(G[j], rowp, g, fxc[j], gy_, gyw, fyc, cv[j], prm.dt, prm.speed, err);
             g_ow = ow;
         }
     };
     if (PIPE) issue_row(out_lo - DEPTH);
 
-    for (int ly = out_lo - DEPTH; ly < out_hi + DEPTH; ++ly) {
+    // one row: slot K holds the OLDER row of every window, K + 1 the middle one, K + 2 receives the newest.
+    // ROT (the PIPE variant, 168 registers): the roles rotate; otherwise (128 registers, small grids) the slots are
+    // fixed and the rows move down one slot after every row, which needs fewer live registers.
+    constexpr bool ROT = PIPE;
+    auto row = [&](auto kc, const int ly) {
+        constexpr int K0 = ROT ? decltype(kc)::value % 3 : 0, K1 = (K0 + 1) % 3, K2 = (K0 + 2) % 3;
+        float2 (&A0)[4] = A[K0]; float2 (&A1)[4] = A[K1]; float2 (&An)[4] = A[K2];
+        float (&W0)[4] = Wv[K0]; float (&W1)[4] = Wv[K1]; float (&Wn)[4] = Wv[K2];
+        float2 (&B0)[4] = B[K0]; float2 (&B1)[4] = B[K1]; float2 (&Bn)[4] = B[K2];
         const int gy = g.y0 + ly;
+        // the clamp-to-edge fix-ups below only fire next to the grid's first / last row: one warp-uniform branch
+        // keeps their 64 selects off every other row
+        const bool near_edge = gy <= DEPTH + 1 || gy >= g.hg - 1;
         // ---- stage 0: advect row ly (ref: shader.AdvectVelocity.comp:27-50).  All 4 cells are traced
         // without branching (16 independent gathers in flight); solid cells are zeroed afterwards.
-        float2 An[4];
-        if (PIPE) {
+        if (!PIPE) issue_row(ly);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                An[j] = (g_valid && !((g_ow >> (8 * j)) & 0xffu)) ? gather_finish(G[j], prm.diss) : make_float2(0.0f, 0.0f);
-            issue_row(ly + 1);
-        } else {
-            const uint32_t ow = ow_n;
-            const float4 c01 = c01_n, c23 = c23_n;
-            fetch_row(ly + 1);
-            if (gy >= 0 && gy < g.hg) {
-                const float2 cv[4] = {make_float2(c01.x, c01.y), make_float2(c01.z, c01.w), make_float2(c23.x, c23.y),
-                                      make_float2(c23.z, c23.w)};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) An[j] = advect_gather<SLAB>(vin, g, xc0 + j, gy, cv[j], prm.dt, prm.speed, prm.diss, err);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if ((ow >> (8 * j)) & 0xffu) An[j] = make_float2(0.0f, 0.0f);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) An[j] = make_float2(0.0f, 0.0f);
-            }
-        }
+        for (int j = 0; j < 4; ++j)
+            An[j] = (g_valid && !((g_ow >> (8 * j)) & 0xffu)) ? gather_finish(G[j], prm.diss) : make_float2(0.0f, 0.0f);
+        if (PIPE) issue_row(ly + 1);
 
         // ---- stage 1: vorticity of row r1 = ly-1 (ref: shader.CalcVorticity.comp:20-26)
         // clamp-to-edge in y: at the first / last grid row the missing neighbour row is the row itself
         const int r1 = ly - 1, g1 = gy - 1;
-        if (g1 == 0) copy4(A0, A1);
-        if (g1 == g.hg - 1) copy4(An, A1);
-        float Wn[4];
+        if (near_edge) {
+            if (g1 == 0) copy4(A0, A1);
+            if (g1 == g.hg - 1) copy4(An, A1);
+        }
         {
             const float ly_ = bitsel(A1[0].y, __shfl_sync(FULL, A1[3].y, lane_l), edge_l);
             const float ry_ = bitsel(A1[3].y, __shfl_sync(FULL, A1[0].y, lane_r), edge_r);
@@ -216,9 +218,10 @@ k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, fl
 
         // ---- stage 2: confinement on row r2 = ly-2 (ref: shader.ApplyVorticity.comp:26-39)
         const int g2 = gy - 2;
-        if (g2 == 0) copy4(W0, W1);
-        if (g2 == g.hg - 1) copy4(Wn, W1);
-        float2 Bn[4];
+        if (near_edge) {
+            if (g2 == 0) copy4(W0, W1);
+            if (g2 == g.hg - 1) copy4(Wn, W1);
+        }
         {
             const float wl = bitsel(W1[0], __shfl_sync(FULL, W1[3], lane_l), edge_l);
             const float wr = bitsel(W1[3], __shfl_sync(FULL, W1[0], lane_r), edge_r);
@@ -232,12 +235,14 @@ k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, fl
         }
 
         // ---- stage 3 (optional): viscosity on row r3 = ly-3 (ref: shader.Viscosity.comp:24-31)
-        float2 Fn[4];           // newest row of the final pre-projection velocity
-        int rF;                 // its local row
+        float2 (&Fn)[4] = VISCOUS ? C[K2] : B[K2];           // newest row of the final pre-projection velocity
+        const int rF = VISCOUS ? ly - 3 : ly - 2;            // its local row
         if (VISCOUS) {
             const int g3 = gy - 3;
-            if (g3 == 0) copy4(B0, B1);
-            if (g3 == g.hg - 1) copy4(Bn, B1);
+            if (near_edge) {
+                if (g3 == 0) copy4(B0, B1);
+                if (g3 == g.hg - 1) copy4(Bn, B1);
+            }
             const float lx = bitsel(B1[0].x, __shfl_sync(FULL, B1[3].x, lane_l), edge_l);
             const float ly2 = bitsel(B1[0].y, __shfl_sync(FULL, B1[3].y, lane_l), edge_l);
             const float rx = bitsel(B1[3].x, __shfl_sync(FULL, B1[0].x, lane_r), edge_r);
@@ -249,10 +254,6 @@ k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, fl
                 Fn[j].x = (x1.x + x2.x + B0[j].x + Bn[j].x + B1[j].x * prm.alpha) * prm.rbeta;
                 Fn[j].y = (x1.y + x2.y + B0[j].y + Bn[j].y + B1[j].y * prm.alpha) * prm.rbeta;
             }
-            rF = ly - 3;
-        } else {
-            copy4(Fn, Bn);
-            rF = ly - 2;
         }
         if (st_ok && rF >= out_lo && rF < out_hi) {
             float4* dst = reinterpret_cast<float4*>(vout + lin(g, xa, rF));
@@ -262,12 +263,14 @@ k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, fl
 
         // ---- stage 4: divergence + blocked-neighbour mask of row rd = rF-1
         //      (ref: shader.Divergence.comp:22-40; mask bits as in stages_ref.cu k_divergence)
-        float2 (&F0)[4] = VISCOUS ? C0 : B0;      // row rd-1
-        float2 (&F1)[4] = VISCOUS ? C1 : B1;      // row rd
+        float2 (&F0)[4] = VISCOUS ? C[K0] : B[K0];      // row rd-1
+        float2 (&F1)[4] = VISCOUS ? C[K1] : B[K1];      // row rd
         const int rd = rF - 1, gd = g.y0 + rd;
         if (rd >= out_lo && rd < out_hi) {
-            if (gd == 0) copy4(F0, F1);
-            if (gd == g.hg - 1) copy4(Fn, F1);
+            if (near_edge) {
+                if (gd == 0) copy4(F0, F1);
+                if (gd == g.hg - 1) copy4(Fn, F1);
+            }
             const uint32_t oM = *reinterpret_cast<const uint32_t*>(obs + lin(g, xc0, rd));
             const uint32_t oB = *reinterpret_cast<const uint32_t*>(obs + lin(g, xc0, max(gd - 1, 0) - g.y0));
             const uint32_t oT = *reinterpret_cast<const uint32_t*>(obs + lin(g, xc0, min(gd + 1, g.hg - 1) - g.y0));
@@ -297,17 +300,46 @@ k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, fl
                 if (sT || gd == g.hg - 1) m |= NB_T;
                 mword |= m << (8 * j);
             }
+            // the scaled copy the Jacobi kernels read (common.cuh NB_RAW): 0.25 b, exact for every b but a non-zero
+            // |b| < 2^-124 - those cells keep b and carry the NB_RAW bit
+            const float2 q = make_float2(0.25f, 0.25f), four = make_float2(4.0f, 4.0f);
+            float2 s01 = __fmul2_rn(make_float2(dv[0], dv[1]), q), s23 = __fmul2_rn(make_float2(dv[2], dv[3]), q);
+            const float2 u01 = __fmul2_rn(s01, four), u23 = __fmul2_rn(s23, four);
+            if (((__float_as_uint(u01.x) ^ __float_as_uint(dv[0])) | (__float_as_uint(u01.y) ^ __float_as_uint(dv[1])) |
+                 (__float_as_uint(u23.x) ^ __float_as_uint(dv[2])) | (__float_as_uint(u23.y) ^ __float_as_uint(dv[3]))) != 0u) {
+                float sc[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    bool raw;
+                    sc[j] = scaled_divergence(dv[j], &raw);
+                    if (raw) mword |= (uint32_t)NB_RAW << (8 * j);
+                }
+                s01 = make_float2(sc[0], sc[1]);
+                s23 = make_float2(sc[2], sc[3]);
+            }
             if (st_ok) {
                 stg_stream(reinterpret_cast<float4*>(div + lin(g, xa, rd)), make_float4(dv[0], dv[1], dv[2], dv[3]));
+                stg_stream(reinterpret_cast<float4*>(div4 + lin(g, xa, rd)), make_float4(s01.x, s01.y, s23.x, s23.y));
                 *reinterpret_cast<uint32_t*>(nbmask + lin(g, xa, rd)) = mword;
             }
         }
+        if (!ROT) {
+            copy4(A[0], A[1]); copy4(A[1], A[2]);
+            copy4(Wv[0], Wv[1]); copy4(Wv[1], Wv[2]);
+            copy4(B[0], B[1]); copy4(B[1], B[2]);
+            if (VISCOUS) { copy4(C[0], C[1]); copy4(C[1], C[2]); }
+        }
+    };
 
-        // ---- roll the windows
-        copy4(A0, A1); copy4(A1, An);
-        copy4(W0, W1); copy4(W1, Wn);
-        copy4(B0, B1); copy4(B1, Bn);
-        if (VISCOUS) { copy4(C0, C1); copy4(C1, Fn); }
+    if (ROT) {
+        // rows beyond out_hi + DEPTH - 1 (at most two, to complete a group of three) load and store nothing
+        for (int ly = out_lo - DEPTH; ly < out_hi + DEPTH; ly += 3) {
+            row(std::integral_constant<int, 0>{}, ly);
+            row(std::integral_constant<int, 1>{}, ly + 1);
+            row(std::integral_constant<int, 2>{}, ly + 2);
+        }
+    } else {
+        for (int ly = out_lo - DEPTH; ly < out_hi + DEPTH; ++ly) row(std::integral_constant<int, 0>{}, ly);
     }
 }
 
@@ -549,7 +581,10 @@ k_gradient_mask4(const float2* __restrict__ vin, const float* __restrict__ p, co
 
 }  // namespace
 
-bool preproject_supported(const Geom& g) { return g.w % 4 == 0 && g.w >= 8; }
+bool preproject_supported(const Geom& g) {
+    // the gathers use 32-bit cell offsets: global row x width must stay below 2^31
+    return g.w % 4 == 0 && g.w >= 8 && (size_t)g.w * (size_t)g.hg < ((size_t)1 << 31);
+}
 
 int launch_zero_borders(float2* vel, Geom g, int r0, int r1, cudaStream_t st) {
     if (r1 <= r0) return 0;
@@ -558,8 +593,8 @@ int launch_zero_borders(float2* vel, Geom g, int r0, int r1, cudaStream_t st) {
     return 1;
 }
 
-int launch_preproject(const float2* vin, const uint8_t* obs, float2* vout, float* vort, float* div, uint8_t* nbmask,
-                      Geom g, int r0, int r1, float dt, float speed, float diss, float scale, bool viscous, float alpha,
+int launch_preproject(const float2* vin, const uint8_t* obs, float2* vout, float* vort, float* div, float* div4,
+                      uint8_t* nbmask, Geom g, int r0, int r1, float dt, float speed, float diss, float scale, bool viscous, float alpha,
                       float rbeta, int sm_count, int* err, cudaStream_t st) {
     if (r1 <= r0) return 0;
     PreParams prm;
@@ -571,7 +606,7 @@ int launch_preproject(const float2* vin, const uint8_t* obs, float2* vout, float
     // with more, lighter CTAs (measured: 640x360 and 1024^2 vs 4096^2 and 32768x4096)
     static const int pipe_env = [] { const char* e = getenv("NATRIX_PRE_PIPE"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
     const bool pipe = pipe_env >= 0 ? pipe_env != 0 : (size_t)g.w * (size_t)(r1 - r0) >= ((size_t)4 << 20);
-    const int warps = pipe ? 12 : PWARPS, resident = pipe ? 1 : 2;
+    const int warps = 12, resident = 1;
     int nchunks = (sm_count * warps * resident) / prm.nstrips;  // one tile per resident warp
     if (nchunks < 1) nchunks = 1;
     int ch = (rows + nchunks - 1) / nchunks;
@@ -582,7 +617,7 @@ int launch_preproject(const float2* vin, const uint8_t* obs, float2* vout, float
     prm.ntiles = prm.nstrips * nchunks;
     const int blocks = (prm.ntiles + warps - 1) / warps;
     const bool slab = g.hl != g.hg;
-#define NATRIX_PRE(V, S, P) k_preproject<V, S, P><<<blocks, warps * 32, 0, st>>>(vin, obs, vout, vort, div, nbmask, g, prm, err)
+#define NATRIX_PRE(V, S, P) k_preproject<V, S, P><<<blocks, warps * 32, 0, st>>>(vin, obs, vout, vort, div, div4, nbmask, g, prm, err)
     if (pipe) {
         if (viscous) { if (slab) NATRIX_PRE(true, true, true); else NATRIX_PRE(true, false, true); }
         else { if (slab) NATRIX_PRE(false, true, true); else NATRIX_PRE(false, false, true); }

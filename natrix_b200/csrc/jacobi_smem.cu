@@ -12,8 +12,9 @@
 // is ~2 000 cycles, and depth can go to 16 (the halo of `depth` cells per side is recomputed; compute is cheap
 // when the grid fits a single wave of blocks).
 //
-// Arithmetic and operand order are those of every other Jacobi kernel here - ((x1 + x2) + y1) + y2 - b, then
-// * 0.25, centre substituted for blocked neighbours - so results are bit-identical.  Cells of the padded tile that
+// Arithmetic and operand order are those of every other Jacobi kernel here - ((x1 + x2) + y1) + y2, then
+// fma(sum, 0.25, -b4) on the pre-scaled divergence (== (sum - b) * 0.25, common.cuh NB_RAW), centre substituted
+// for blocked neighbours - so results are bit-identical.  Cells of the padded tile that
 // lie outside the grid (or outside the rows the slab holds) are zero with all four neighbours blocked: they stay
 // zero and nothing in the grid ever reads them, because every in-grid cell next to the edge carries the blocked
 // bit for that direction (the shader's clamp-to-edge rule, written into the mask by the divergence stage).
@@ -31,7 +32,7 @@ constexpr int SM_MAX_PW = 128;              // padded tile width: one warp cover
 
 struct SmemParams {
     const float* pin;
-    const float* div;
+    const float* div;       // the pre-scaled divergence
     const uint8_t* nbm;
     float* pout;
     int w;
@@ -48,7 +49,8 @@ __device__ __forceinline__ float jacobi_cell(float c, float l, float r, float b,
     const float x2 = (m & NB_R) ? c : r;
     const float y1 = (m & NB_B) ? c : b;
     const float y2 = (m & NB_T) ? c : t;
-    return (x1 + x2 + y1 + y2 - d) * 0.25f;
+    const float sum = x1 + x2 + y1 + y2;
+    return (m & NB_RAW) ? (sum - d) * 0.25f : __fmaf_rn(sum, 0.25f, -d);     // d is 0.25 b, or b itself under NB_RAW
 }
 
 // VEC: width % 4 == 0, so a lane's 4 columns are inside or outside the grid together and global accesses are
@@ -137,10 +139,10 @@ k_jacobi_smem(const SmemParams prm) {
                 n.z = jacobi_cell(c.z, c.y, c.w, b.z, t.z, d.z, m >> 16);
                 n.w = jacobi_cell(c.w, c.z, r, b.w, t.w, d.w, m >> 24);
             } else {
-                n.x = (l + c.y + b.x + t.x - d.x) * 0.25f;
-                n.y = (c.x + c.z + b.y + t.y - d.y) * 0.25f;
-                n.z = (c.y + c.w + b.z + t.z - d.z) * 0.25f;
-                n.w = (c.z + r + b.w + t.w - d.w) * 0.25f;
+                n.x = __fmaf_rn(l + c.y + b.x + t.x, 0.25f, -d.x);
+                n.y = __fmaf_rn(c.x + c.z + b.y + t.y, 0.25f, -d.y);
+                n.z = __fmaf_rn(c.y + c.w + b.z + t.z, 0.25f, -d.z);
+                n.w = __fmaf_rn(c.z + r + b.w + t.w, 0.25f, -d.w);
             }
             if (lane_on) *reinterpret_cast<float4*>(dst + o) = n;
         }
@@ -185,13 +187,13 @@ size_t jacobi_smem_cell_limit() {
     return n;
 }
 
-int launch_jacobi_smem(const float* pin, const float* div, const uint8_t* nbmask, float* pout, Geom g, int depth,
+int launch_jacobi_smem(const float* pin, const float* div4, const uint8_t* nbmask, float* pout, Geom g, int depth,
                        int r0, int r1, bool p_is_zero, int sm_count, cudaStream_t st) {
     if (r1 <= r0) return 0;
     if (depth < 1 || depth > 16) return -1;
     static const size_t smem_cap = (size_t)env_int("NATRIX_SMEM_KB", 200) * 1024;
     SmemParams prm;
-    prm.pin = pin; prm.div = div; prm.nbm = nbmask; prm.pout = pout;
+    prm.pin = pin; prm.div = div4; prm.nbm = nbmask; prm.pout = pout;
     prm.w = g.w;
     prm.row_lo = std::max(-g.halo, -g.y0);
     prm.row_hi = std::min(g.hl + g.halo, g.hg - g.y0);

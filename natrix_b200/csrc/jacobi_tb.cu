@@ -24,7 +24,11 @@
 // bit for that direction and substitutes its own pressure (the shader's clamp-to-edge rule).
 //
 // Obstacles.  Warps whose rows in flight have an all-zero mask run a select-free body
-// (5 FP instructions per cell-sweep); otherwise a body with 4 selects per cell.
+// (4 FP instructions per cell-sweep); otherwise a body with 4 selects per cell.
+//
+// Scaled divergence.  The kernel reads b4 = 0.25 b (written next to the divergence by the stage that computes it)
+// and ends a sweep in one fused multiply-add, fma(sum, 0.25, -b4), bit-identical to the shader's (sum - b) * 0.25;
+// cells where 0.25 b would be inexact carry NB_RAW in the mask and take the two-step form (common.cuh).
 #include <cuda.h>
 
 #include <algorithm>
@@ -184,7 +188,9 @@ __device__ __forceinline__ void row_step(float (&a)[T][2][4], const LaneAddr& sa
                 y1 = (bits & NB_B) ? C : y1;
                 y2 = (bits & NB_T) ? C : y2;
             }
-            res[j] = (x1 + x2 + y1 + y2 - d[j]) * 0.25f;
+            const float sum = x1 + x2 + y1 + y2;
+            res[j] = __fmaf_rn(sum, 0.25f, -d[j]);
+            if (SLOW && ((mrow_bits >> (8 * j)) & NB_RAW)) res[j] = (sum - d[j]) * 0.25f;    // d holds b itself here
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) { old[c] = nw[c]; nw[c] = res[c]; }
@@ -201,11 +207,30 @@ __device__ __forceinline__ void row_step(float (&a)[T][2][4], const LaneAddr& sa
 // already pair-aligned: 2 + 4 instructions per 2 cells instead of 10.
 __device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
 
-template <int T, bool PZERO, int PAR, bool SLOW>
+// A/B switches for timing experiments only (scripts/ab_build.sh); the shipped library is built with the defaults.
+// NATRIX_TB_FMA=0 ends a sweep in add + multiply on the SCALED divergence: same instruction mix as the unfused
+// form, wrong numbers.
+#ifndef NATRIX_TB_FMA
+#define NATRIX_TB_FMA 1
+#endif
+#ifndef NATRIX_TB_FILL
+#define NATRIX_TB_FILL 0      // measured: the fill bodies are cold code (instruction-cache misses) and cost what they save
+#endif
+// the last two operations of a sweep on a pair of cells: fma(sum, 0.25, -b4) == (sum - b) * 0.25 (common.cuh NB_RAW)
+__device__ __forceinline__ float2 finish2(float2 sum, float2 b4) {
+#if NATRIX_TB_FMA
+    return __ffma2_rn(sum, make_float2(0.25f, 0.25f), neg2(b4));
+#else
+    return __fmul2_rn(__fadd2_rn(sum, neg2(b4)), make_float2(0.25f, 0.25f));
+#endif
+}
+
+// RAW: some cell of the rows in flight carries NB_RAW (its ring entry is b itself, not 0.25 b): those cells redo the
+// last step in the shader's two-step form.  Practically never instantiated at run time (a non-zero |b| < 2^-124).
+template <int T, bool PZERO, int PAR, bool SLOW, bool RAW = false>
 __device__ __forceinline__ void row_step2(float2 (&a)[T][2][2], const LaneAddr& sa, int i, int lane,
                                           float2 (&out)[2]) {
     constexpr unsigned FULL = 0xffffffffu;
-    const float2 quarter = make_float2(0.25f, 0.25f);
     float2 nw[2];
     if (PZERO) {
         nw[0] = nw[1] = make_float2(0.0f, 0.0f);
@@ -223,8 +248,10 @@ __device__ __forceinline__ void row_step2(float2 (&a)[T][2][2], const LaneAddr& 
         const float sl = bitsel(mid[0].x, __shfl_sync(FULL, mid[1].y, lane_l), sa.edge_l);
         const float sr = bitsel(mid[1].y, __shfl_sync(FULL, mid[0].x, lane_r), sa.edge_r);
         float2 s0, s1, y10 = old[0], y11 = old[1], y20 = nw[0], y21 = nw[1];
+        uint32_t raw = 0u;
         if (SLOW) {
             const uint32_t m = mask_of_row(sa, i - t);
+            if (RAW) raw = m & (0x01010101u * NB_RAW);
             const float c0 = mid[0].x, c1 = mid[0].y, c2 = mid[1].x, c3 = mid[1].y;
             s0.x = ((m & (NB_L << 0)) ? c0 : sl) + ((m & (NB_R << 0)) ? c0 : c1);
             s0.y = ((m & (NB_L << 8)) ? c1 : c0) + ((m & (NB_R << 8)) ? c1 : c2);
@@ -238,9 +265,16 @@ __device__ __forceinline__ void row_step2(float2 (&a)[T][2][2], const LaneAddr& 
             s0 = make_float2(sl + mid[0].y, mid[0].x + mid[1].x);
             s1 = make_float2(mid[0].y + mid[1].y, mid[1].x + sr);
         }
-        // ((x1 + x2) + y1) + y2 - b, then * 0.25: the shader's left-to-right order
-        const float2 r0 = __fmul2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(s0, y10), y20), neg2(make_float2(dv.x, dv.y))), quarter);
-        const float2 r1 = __fmul2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(s1, y11), y21), neg2(make_float2(dv.z, dv.w))), quarter);
+        // ((x1 + x2) + y1) + y2 in the shader's left-to-right order, then fma(sum, 0.25, -b4) == (sum - b) * 0.25
+        const float2 t0 = __fadd2_rn(__fadd2_rn(s0, y10), y20), t1 = __fadd2_rn(__fadd2_rn(s1, y11), y21);
+        float2 r0 = finish2(t0, make_float2(dv.x, dv.y));
+        float2 r1 = finish2(t1, make_float2(dv.z, dv.w));
+        if (SLOW && RAW && raw) {                        // the ring holds b itself for these cells
+            if (raw & (NB_RAW << 0)) r0.x = (t0.x - dv.x) * 0.25f;
+            if (raw & (NB_RAW << 8)) r0.y = (t0.y - dv.y) * 0.25f;
+            if (raw & (NB_RAW << 16)) r1.x = (t1.x - dv.z) * 0.25f;
+            if (raw & (NB_RAW << 24)) r1.y = (t1.y - dv.w) * 0.25f;
+        }
         old[0] = nw[0]; old[1] = nw[1];
         nw[0] = r0; nw[1] = r1;
     }
@@ -250,13 +284,12 @@ __device__ __forceinline__ void row_step2(float2 (&a)[T][2][2], const LaneAddr& 
 // Select-free packed row step in two phases.  Phase A forms (x1 + x2) + y1 of EVERY level from the rows
 // kept from earlier iterations - nothing in it depends on this iteration's new rows, and after it the
 // "older" slot of every level is dead.  Phase B is the short dependent chain through the levels
-// (+ y2, - b, * 0.25): each level's new row can be written straight into the dead slot of the level
+// (+ y2, then fma(., 0.25, -b4)): each level's new row can be written straight into the dead slot of the level
 // below, so the state rotates without register moves.
 template <int T, bool PZERO, int PAR>
 __device__ __forceinline__ void row_step2_fast(float2 (&a)[T][2][2], const LaneAddr& sa, int i, int lane,
                                                float2 (&out)[2]) {
     constexpr unsigned FULL = 0xffffffffu;
-    const float2 quarter = make_float2(0.25f, 0.25f);
     const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
     float2 part[T][2];
 #pragma unroll
@@ -281,8 +314,8 @@ __device__ __forceinline__ void row_step2_fast(float2 (&a)[T][2][2], const LaneA
 #pragma unroll
     for (int t = 1; t <= T; ++t) {
         const float4 dv = lds128(sa.d + (uint32_t)((i - t) & (D_ROWS - 1)) * (SW * 4));
-        const float2 r0 = __fmul2_rn(__fadd2_rn(__fadd2_rn(part[t - 1][0], nw0), neg2(make_float2(dv.x, dv.y))), quarter);
-        const float2 r1 = __fmul2_rn(__fadd2_rn(__fadd2_rn(part[t - 1][1], nw1), neg2(make_float2(dv.z, dv.w))), quarter);
+        const float2 r0 = finish2(__fadd2_rn(part[t - 1][0], nw0), make_float2(dv.x, dv.y));
+        const float2 r1 = finish2(__fadd2_rn(part[t - 1][1], nw1), make_float2(dv.z, dv.w));
         a[t - 1][PAR][0] = nw0;
         a[t - 1][PAR][1] = nw1;
         nw0 = r0;
@@ -301,7 +334,6 @@ template <int T, bool PZERO, int PAR, int LV>
 __device__ __forceinline__ void row_step2_fill(float2 (&a)[T][2][2], const LaneAddr& sa, int i, int lane) {
     static_assert(LV < T, "the fill body stops below the last level");
     constexpr unsigned FULL = 0xffffffffu;
-    const float2 quarter = make_float2(0.25f, 0.25f);
     const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
     float2 part[LV > 0 ? LV : 1][2];
 #pragma unroll
@@ -326,8 +358,8 @@ __device__ __forceinline__ void row_step2_fill(float2 (&a)[T][2][2], const LaneA
 #pragma unroll
     for (int t = 1; t <= LV; ++t) {
         const float4 dv = lds128(sa.d + (uint32_t)((i - t) & (D_ROWS - 1)) * (SW * 4));
-        const float2 r0 = __fmul2_rn(__fadd2_rn(__fadd2_rn(part[t - 1][0], nw0), neg2(make_float2(dv.x, dv.y))), quarter);
-        const float2 r1 = __fmul2_rn(__fadd2_rn(__fadd2_rn(part[t - 1][1], nw1), neg2(make_float2(dv.z, dv.w))), quarter);
+        const float2 r0 = finish2(__fadd2_rn(part[t - 1][0], nw0), make_float2(dv.x, dv.y));
+        const float2 r1 = finish2(__fadd2_rn(part[t - 1][1], nw1), make_float2(dv.z, dv.w));
         a[t - 1][PAR][0] = nw0;
         a[t - 1][PAR][1] = nw1;
         nw0 = r0;
@@ -338,11 +370,10 @@ __device__ __forceinline__ void row_step2_fill(float2 (&a)[T][2][2], const LaneA
 }
 
 // Rows deep inside an obstacle: every cell of the strip has all four neighbours blocked, in every row in
-// flight, so each level is ((C + C) + C) + C - b, * 0.25 of the cell itself (shader.Poisson.comp:32-37 with
-// all four substitutions): no neighbours, no shuffles, no selects.
+// flight (and none carries NB_RAW), so each level is ((C + C) + C) + C - b, * 0.25 of the cell itself
+// (shader.Poisson.comp:32-37 with all four substitutions): no neighbours, no shuffles, no selects.
 template <int T, bool PZERO, int PAR>
 __device__ __forceinline__ void row_step2_solid(float2 (&a)[T][2][2], const LaneAddr& sa, int i, float2 (&out)[2]) {
-    const float2 quarter = make_float2(0.25f, 0.25f);
     float2 nw0, nw1;
     if (PZERO) {
         nw0 = nw1 = make_float2(0.0f, 0.0f);
@@ -355,8 +386,8 @@ __device__ __forceinline__ void row_step2_solid(float2 (&a)[T][2][2], const Lane
     for (int t = 1; t <= T; ++t) {
         const float2 c0 = a[t - 1][PAR ^ 1][0], c1 = a[t - 1][PAR ^ 1][1];
         const float4 dv = lds128(sa.d + (uint32_t)((i - t) & (D_ROWS - 1)) * (SW * 4));
-        const float2 r0 = __fmul2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(c0, c0), c0), c0), neg2(make_float2(dv.x, dv.y))), quarter);
-        const float2 r1 = __fmul2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(c1, c1), c1), c1), neg2(make_float2(dv.z, dv.w))), quarter);
+        const float2 r0 = finish2(__fadd2_rn(__fadd2_rn(__fadd2_rn(c0, c0), c0), c0), make_float2(dv.x, dv.y));
+        const float2 r1 = finish2(__fadd2_rn(__fadd2_rn(__fadd2_rn(c1, c1), c1), c1), make_float2(dv.z, dv.w));
         a[t - 1][PAR][0] = nw0;
         a[t - 1][PAR][1] = nw1;
         nw0 = r0;
@@ -379,7 +410,6 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
 
     const int4 td = prm.tiles[tile];
     const int strip = td.x, out_lo = td.y, out_hi = td.z;
-    if (prm.trace && lane == 0) { prm.trace[4 * tile] = globaltimer_ns(); prm.trace[4 * tile + 2] = smid(); }
     const int x0 = strip * (SW - 2 * prm.hx) - prm.hx;      // first strip column (may be < 0)
     const int y_first = out_lo - T;                          // first input row (local)
     const int nrows = (out_hi - out_lo) + 2 * T;
@@ -412,6 +442,8 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
     // never overtakes the readers of its output buffer.  Both are no-ops in a plain launch.
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // per-tile trace (NATRIX_TB_TRACE): the clock starts once the tile may touch the fields
+    if (prm.trace && lane == 0) { prm.trace[4 * tile] = globaltimer_ns(); prm.trace[4 * tile + 2] = smid(); }
     if (lane == 0) issue(0);
 
     float a[PACKED ? 1 : T][2][4];                    // scalar state
@@ -432,7 +464,7 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
     const uint32_t edge_l = xa == 0 ? 0xffffffffu : 0u, edge_r = xa + 4 == prm.w ? 0xffffffffu : 0u;
     // the grid-edge L / R bits are honoured through edge_l / edge_r, so they need not make a row busy
     const LaneAddr sa{p_addr + 16u * lane, d_addr + 16u * lane, m_addr + (uint32_t)(x0 & 15) + 4u * lane, edge_l, edge_r,
-                      0x0f0f0f0fu & ~((edge_l & (uint32_t)NB_L) | (edge_r & ((uint32_t)NB_R << 24)))};
+                      0x1f1f1f1fu & ~((edge_l & (uint32_t)NB_L) | (edge_r & ((uint32_t)NB_R << 24)))};
     const bool st_ok = 4 * lane >= prm.hx && 4 * lane < SW - prm.hx && xa < prm.w;
     float* const out_col = prm.pout + xa;
 
@@ -442,6 +474,7 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
             stg_stream(reinterpret_cast<float4*>(out_col + (ptrdiff_t)ly * prm.w), make_float4(r0, r1, r2, r3));
     };
     uint32_t solid = 0u;                              // bit t-1: every cell of row i-t (whole strip) is fully blocked
+    uint32_t rawb = 0u;                               // bit t-1: some cell of row i-t carries NB_RAW
     auto fast_row = [&](auto par, int i) {            // no row in flight has mask bits
         constexpr int PAR = decltype(par)::value;
         if constexpr (PACKED) {
@@ -461,6 +494,7 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
         } else if constexpr (PACKED) {
             float2 r[2];
             if (solid == BUSY_MASK) row_step2_solid<T, PZERO, PAR>(a2, sa, i, r);
+            else if (rawb) row_step2<T, PZERO, PAR, true, true>(a2, sa, i, lane, r);
             else row_step2<T, PZERO, PAR, true>(a2, sa, i, lane, r);
             store_row(i, r[0].x, r[0].y, r[1].x, r[1].y);
         } else {
@@ -472,7 +506,7 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
     using I0 = std::integral_constant<int, 0>;
     using I1 = std::integral_constant<int, 1>;
     // groups whose four rows all lie in the fill phase (input rows < 2 T): T / 2 of them
-    constexpr int FILL_GROUPS = PACKED ? T / 2 : 0;
+    constexpr int FILL_GROUPS = (PACKED && NATRIX_TB_FILL) ? T / 2 : 0;
     auto fill_rows = [&](auto gc, int i0) {           // the four rows of fill group G = decltype(gc)::value
         constexpr int G = decltype(gc)::value;
         if constexpr (PACKED && G < FILL_GROUPS) {
@@ -505,23 +539,27 @@ k_jacobi_tb(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ C
         if (lane == 0 && g + 1 < ngroups) issue(g + 1);
         if (busy | a0 | a1 | a2_ | a3) {
             // some row in flight (or arriving) carries mask bits: per row, the body its rows in flight need
-            constexpr uint32_t ALL = 0x0f0f0f0fu;
-            const uint32_t s0 = __all_sync(0xffffffffu, (w0 & ALL) == ALL) ? 1u : 0u, s1 = __all_sync(0xffffffffu, (w1 & ALL) == ALL) ? 1u : 0u;
-            const uint32_t s2 = __all_sync(0xffffffffu, (w2 & ALL) == ALL) ? 1u : 0u, s3 = __all_sync(0xffffffffu, (w3 & ALL) == ALL) ? 1u : 0u;
+            constexpr uint32_t ALL = 0x0f0f0f0fu, BITS = 0x1f1f1f1fu, RAWS = 0x01010101u * NB_RAW;
+            // solid: all four neighbours blocked and no NB_RAW, in every cell of the strip
+            const uint32_t s0 = __all_sync(0xffffffffu, (w0 & BITS) == ALL) ? 1u : 0u, s1 = __all_sync(0xffffffffu, (w1 & BITS) == ALL) ? 1u : 0u;
+            const uint32_t s2 = __all_sync(0xffffffffu, (w2 & BITS) == ALL) ? 1u : 0u, s3 = __all_sync(0xffffffffu, (w3 & BITS) == ALL) ? 1u : 0u;
+            const uint32_t q = __ballot_sync(0xffffffffu, ((w0 | w1 | w2 | w3) & RAWS) != 0u) ? 1u : 0u;   // per group is enough
             one_row(I0{}, i0);
-            busy = ((busy << 1) | a0) & BUSY_MASK; solid = ((solid << 1) | s0) & BUSY_MASK;
+            busy = ((busy << 1) | a0) & BUSY_MASK; solid = ((solid << 1) | s0) & BUSY_MASK; rawb = ((rawb << 1) | q) & BUSY_MASK;
             one_row(I1{}, i0 + 1);
-            busy = ((busy << 1) | a1) & BUSY_MASK; solid = ((solid << 1) | s1) & BUSY_MASK;
+            busy = ((busy << 1) | a1) & BUSY_MASK; solid = ((solid << 1) | s1) & BUSY_MASK; rawb = ((rawb << 1) | q) & BUSY_MASK;
             one_row(I0{}, i0 + 2);
-            busy = ((busy << 1) | a2_) & BUSY_MASK; solid = ((solid << 1) | s2) & BUSY_MASK;
+            busy = ((busy << 1) | a2_) & BUSY_MASK; solid = ((solid << 1) | s2) & BUSY_MASK; rawb = ((rawb << 1) | q) & BUSY_MASK;
             one_row(I1{}, i0 + 3);
-            busy = ((busy << 1) | a3) & BUSY_MASK; solid = ((solid << 1) | s3) & BUSY_MASK;
+            busy = ((busy << 1) | a3) & BUSY_MASK; solid = ((solid << 1) | s3) & BUSY_MASK; rawb = ((rawb << 1) | q) & BUSY_MASK;
         } else if (PACKED && g < FILL_GROUPS) {
             // pipeline fill: input rows 4 g .. 4 g + 3 feed levels 1 .. (4 g + h) / 2 only
             solid = 0u;
+            rawb = 0u;
             fill_group(g, i0);
         } else {
             solid = 0u;
+            rawb = 0u;
 #pragma unroll 1
             for (int h = 0; h < GROUP; h += 2) {
                 fast_row(I0{}, i0 + h);
@@ -954,7 +992,7 @@ bool jacobi_tb_supported(const Geom& g) {
     return g.w % 16 == 0 && g.w >= SW;
 }
 
-int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div, const uint8_t* nbmask, float* pout, Geom g,
+int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div4, const uint8_t* nbmask, float* pout, Geom g,
                      int depth, int r0, int r1, bool p_is_zero, int packed, const int* boxes, int nboxes,
                      cudaStream_t st) {
     if (!tb) return -1;
@@ -966,7 +1004,7 @@ int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div, const uin
     const CUtensorMap* mp = tb->map_for(pin - off, g.w, rows_alloc, 4);
     if (!mp) return -1;
     const CUtensorMap map_p = *mp;            // copy: the cache vector may reallocate
-    const CUtensorMap* md = tb->map_for(div - off, g.w, rows_alloc, 4);
+    const CUtensorMap* md = tb->map_for(div4 - off, g.w, rows_alloc, 4);
     if (!md) return -1;
     const CUtensorMap map_d = *md;
     const CUtensorMap* mm = tb->map_for(nbmask - off, g.w, rows_alloc, 1);
@@ -1006,7 +1044,8 @@ int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div, const uin
         attr_done = true;
     }
     prm.trace = nullptr;
-    const bool tracing = !tb->trace_path.empty() && tb->launch_no++ == tb->trace_launch;
+    const bool tracing = !tb->trace_path.empty() && tb->launch_no == tb->trace_launch;
+    ++tb->launch_no;
     if (tracing && cudaMalloc((void**)&tb->d_trace, (size_t)prm.ntiles * 32) == cudaSuccess) {
         cudaMemsetAsync(tb->d_trace, 0, (size_t)prm.ntiles * 32, st);
         prm.trace = tb->d_trace;

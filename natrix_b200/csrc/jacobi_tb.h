@@ -12,17 +12,18 @@ JacobiTB* jacobi_tb_create();
 void jacobi_tb_destroy(JacobiTB* tb);
 const char* jacobi_tb_error(JacobiTB* tb);
 // The TMA path needs 16-byte row pitches (width % 16 == 0) and width >= 256; other grids use
-// the 1-sweep mask kernel (launch_poisson_mask).
+// the shared-memory kernel (jacobi_smem.cu).
 bool jacobi_tb_supported(const Geom& g);
 
 // Runs `depth` (1..JACOBI_TB_MAX_DEPTH) Jacobi sweeps pin -> pout for local rows [r0, r1).
-// pin / div / nbmask must be valid on rows [r0-depth, r1+depth) clipped to the global domain.
+// div4 is the PRE-SCALED divergence (0.25 b, or b itself where the mask carries NB_RAW: common.cuh).
+// pin / div4 / nbmask must be valid on rows [r0-depth, r1+depth) clipped to the global domain.
 // p_is_zero: pin is known to be all zero (first block of a step), so it is not read.
 // boxes: nboxes x (x0, x1, y0, y1) bounding boxes (global columns, local rows, half-open), or circles
 // encoded as (cx, -1 - radius, cy, 0), of the obstacles stamped this step - a scheduling hint only: tiles are cut shorter where the select body
 // will run; results never depend on it.
 // Returns the number of kernels launched, or -1 on error (see jacobi_tb_error).
-int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div, const uint8_t* nbmask,
+int jacobi_tb_launch(JacobiTB* tb, const float* pin, const float* div4, const uint8_t* nbmask,
                      float* pout, Geom g, int depth, int r0, int r1, bool p_is_zero, int packed,
                      const int* boxes, int nboxes, cudaStream_t st);
 

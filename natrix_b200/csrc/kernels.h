@@ -24,8 +24,12 @@ int launch_confinement(const float2* vin, const float* vort, float2* vout, Geom 
                        float dt, float scale, cudaStream_t st);
 int launch_viscosity(const float2* vin, float2* vout, Geom g, int r0, int r1, float alpha,
                      float rbeta, cudaStream_t st);
-int launch_divergence(const float2* vel, const uint8_t* obs, float* div, uint8_t* nbmask, Geom g,
+// div4 / nbmask (nullable together): the pre-scaled divergence and the blocked-neighbour mask (with the NB_RAW bit)
+// that the temporally blocked Jacobi kernels and the mask-driven gradient read
+int launch_divergence(const float2* vel, const uint8_t* obs, float* div, float* div4, uint8_t* nbmask, Geom g,
                       int r0, int r1, cudaStream_t st);
+// div4 and the NB_RAW bit of the mask re-derived from div (after the host uploaded a divergence or a mask)
+int launch_rescale_divergence(const float* div, float* div4, uint8_t* nbmask, size_t n, cudaStream_t st);
 int launch_poisson_ref(const float* pin, const float* div, const uint8_t* obs, float* pout, Geom g,
                        int r0, int r1, cudaStream_t st);
 int launch_gradient_ref(const float2* vin, const float* p, const uint8_t* obs, float2* vout, Geom g,
@@ -60,11 +64,9 @@ int launch_render_frame(const float* dye, const float4* lut, const float2* vel, 
                         int vh, float tile, cudaStream_t st);
 
 // ---- fused pipeline (fused.cu / jacobi_tb.cu) ----------------------------------------------------
-int launch_poisson_mask(const float* pin, const float* div, const uint8_t* nbmask, float* pout,
-                        Geom g, int r0, int r1, cudaStream_t st);
 // `depth` (1..16) sweeps pin -> pout for rows [r0, r1), one tile per block in shared memory (jacobi_smem.cu): any
 // width, meant for small grids.  Same contract as jacobi_tb_launch; returns launches, or -1 on a launch error.
-int launch_jacobi_smem(const float* pin, const float* div, const uint8_t* nbmask, float* pout, Geom g, int depth,
+int launch_jacobi_smem(const float* pin, const float* div4, const uint8_t* nbmask, float* pout, Geom g, int depth,
                        int r0, int r1, bool p_is_zero, int sm_count, cudaStream_t st);
 int jacobi_smem_max_depth();             // default sweeps per launch (NATRIX_SMEM_DEPTH, <= 16)
 size_t jacobi_smem_cell_limit();         // grids up to this many cells prefer the shared-memory kernel
@@ -73,7 +75,7 @@ int launch_gradient_mask(const float2* vin, const float* p, const uint8_t* nbmas
                          Geom g, int r0, int r1, int* over1, cudaStream_t st);
 // fused advect + vorticity + confinement + [viscosity] + divergence + mask, rows [r0, r1)
 bool preproject_supported(const Geom& g);
-int launch_preproject(const float2* vin, const uint8_t* obs, float2* vout, float* vort, float* div,
+int launch_preproject(const float2* vin, const uint8_t* obs, float2* vout, float* vort, float* div, float* div4,
                       uint8_t* nbmask, Geom g, int r0, int r1, float dt, float speed, float diss, float scale,
                       bool viscous, float alpha, float rbeta, int sm_count, int* err, cudaStream_t st);
 // InitBoundaries restricted to the border cells of rows [r0, r1), in place

@@ -89,7 +89,7 @@ k_viscosity(const float2* __restrict__ vin, float2* __restrict__ vout, Geom g, i
 // the mask-based Jacobi / gradient kernels consume.
 __global__ void __launch_bounds__(BT)
 k_divergence(const float2* __restrict__ vel, const uint8_t* __restrict__ obs, float* __restrict__ div,
-             uint8_t* __restrict__ nbmask, Geom g, int r0, int r1) {
+             float* __restrict__ div4, uint8_t* __restrict__ nbmask, Geom g, int r0, int r1) {
     CELL_PROLOGUE
     const Nbr n = neighbours(g, x, ly);
     const bool sL = obs[n.l] != OBS_FREE, sR = obs[n.r] != OBS_FREE;
@@ -98,16 +98,29 @@ k_divergence(const float2* __restrict__ vel, const uint8_t* __restrict__ obs, fl
     const float x2 = sR ? 0.0f : vel[n.r].x;
     const float y1 = sB ? 0.0f : vel[n.b].y;
     const float y2 = sT ? 0.0f : vel[n.t].y;
-    div[pos] = 0.5f * ((x2 - x1) + (y2 - y1));
+    const float b = 0.5f * ((x2 - x1) + (y2 - y1));
+    div[pos] = b;
     if (nbmask) {
         const int gy = g.y0 + ly;
-        uint8_t m = 0;
+        bool raw;
+        div4[pos] = scaled_divergence(b, &raw);       // what the temporally blocked Jacobi kernels read (common.cuh NB_RAW)
+        uint8_t m = raw ? NB_RAW : 0;
         if (sL || x == 0) m |= NB_L;
         if (sR || x == g.w - 1) m |= NB_R;
         if (sB || gy == 0) m |= NB_B;
         if (sT || gy == g.hg - 1) m |= NB_T;
         nbmask[pos] = m;
     }
+}
+
+// div4 and the NB_RAW bit of the mask from div (see common.cuh), for a divergence or a mask the host uploaded
+__global__ void __launch_bounds__(256)
+k_rescale_divergence(const float* __restrict__ div, float* __restrict__ div4, uint8_t* __restrict__ nbmask, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool raw;
+    div4[i] = scaled_divergence(div[i], &raw);
+    nbmask[i] = (uint8_t)((nbmask[i] & 0x0f) | (raw ? NB_RAW : 0));
 }
 
 // ref: shader.Poisson.comp:24-37 (reads the obstacle map like the shader does)
@@ -121,20 +134,6 @@ k_poisson_ref(const float* __restrict__ pin, const float* __restrict__ div,
     const float x2 = obs[n.r] != OBS_FREE ? p : pin[n.r];
     const float y1 = obs[n.b] != OBS_FREE ? p : pin[n.b];
     const float y2 = obs[n.t] != OBS_FREE ? p : pin[n.t];
-    pout[pos] = (x1 + x2 + y1 + y2 - div[pos]) * 0.25f;
-}
-
-// same sweep driven by the blocked-neighbour mask (13 B/cell instead of 20)
-__global__ void __launch_bounds__(BT)
-k_poisson_mask(const float* __restrict__ pin, const float* __restrict__ div,
-               const uint8_t* __restrict__ nbmask, float* __restrict__ pout, Geom g, int r0, int r1) {
-    CELL_PROLOGUE
-    const uint8_t m = nbmask[pos];
-    const float p = pin[pos];
-    const float x1 = (m & NB_L) ? p : pin[pos - 1];
-    const float x2 = (m & NB_R) ? p : pin[pos + 1];
-    const float y1 = (m & NB_B) ? p : pin[pos - g.w];
-    const float y2 = (m & NB_T) ? p : pin[pos + g.w];
     pout[pos] = (x1 + x2 + y1 + y2 - div[pos]) * 0.25f;
 }
 
@@ -293,22 +292,21 @@ int launch_viscosity(const float2* vin, float2* vout, Geom g, int r0, int r1, fl
     k_viscosity<<<cell_grid(g, r0, r1), CELL_BLOCK, 0, st>>>(vin, vout, g, r0, r1, alpha, rbeta);
     return 1;
 }
-int launch_divergence(const float2* vel, const uint8_t* obs, float* div, uint8_t* nbmask, Geom g, int r0,
+int launch_divergence(const float2* vel, const uint8_t* obs, float* div, float* div4, uint8_t* nbmask, Geom g, int r0,
                       int r1, cudaStream_t st) {
     ROWS_OR_RETURN
-    k_divergence<<<cell_grid(g, r0, r1), CELL_BLOCK, 0, st>>>(vel, obs, div, nbmask, g, r0, r1);
+    k_divergence<<<cell_grid(g, r0, r1), CELL_BLOCK, 0, st>>>(vel, obs, div, div4, nbmask, g, r0, r1);
+    return 1;
+}
+int launch_rescale_divergence(const float* div, float* div4, uint8_t* nbmask, size_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_rescale_divergence<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(div, div4, nbmask, n);
     return 1;
 }
 int launch_poisson_ref(const float* pin, const float* div, const uint8_t* obs, float* pout, Geom g, int r0,
                        int r1, cudaStream_t st) {
     ROWS_OR_RETURN
     k_poisson_ref<<<cell_grid(g, r0, r1), CELL_BLOCK, 0, st>>>(pin, div, obs, pout, g, r0, r1);
-    return 1;
-}
-int launch_poisson_mask(const float* pin, const float* div, const uint8_t* nbmask, float* pout, Geom g,
-                        int r0, int r1, cudaStream_t st) {
-    ROWS_OR_RETURN
-    k_poisson_mask<<<cell_grid(g, r0, r1), CELL_BLOCK, 0, st>>>(pin, div, nbmask, pout, g, r0, r1);
     return 1;
 }
 int launch_gradient_ref(const float2* vin, const float* p, const uint8_t* obs, float2* vout, Geom g, int r0,

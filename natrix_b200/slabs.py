@@ -89,7 +89,8 @@ class CudaSlabEngine:
         self.L.check(self.sim._lib.natrix_comm_stats(self.sim._handle(), C.byref(n), C.byref(b)))
         return n.value, b.value
 
-    FIELD_IDS = {"velocity": 0, "pressure": 1, "divergence": 2, "nbmask": 5}
+    # "divergence" is exchanged as the scaled copy the Jacobi sweeps read (NATRIX_DIV4)
+    FIELD_IDS = {"velocity": 0, "pressure": 1, "divergence": 6, "nbmask": 5}
 
     def push_params(self):
         self.sim._push_params()

@@ -35,7 +35,14 @@ for f in sorted(glob.glob(sys.argv[1] + "/bench*.json")):
 PY
 [ "$MODE" = quick ] && exit 0
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"; echo "ref rc=$?"
-# ---- ncu: launch lists, then --set full captures of the top kernels at the bench sizes
+# ---- ncu: launch lists, then --set full captures of the top kernels at the bench sizes.  gpurun brings back at most
+# 64 MiB: every report is turned into its raw-metric CSV (+ the source page of the hot kernels) on the box and removed.
+keep() {   # keep <name> [source]
+  ncu -i "$OUT/$1.ncu-rep" --page raw --csv > "$OUT/$1.raw.csv" 2>/dev/null
+  ncu -i "$OUT/$1.ncu-rep" --page details > "$OUT/$1.details.txt" 2>/dev/null
+  [ "${2:-}" = source ] && ncu -i "$OUT/$1.ncu-rep" --page source --csv > "$OUT/$1.source.csv" 2>/dev/null
+  rm -f "$OUT/$1.ncu-rep"
+}
 for WL in cfg5 cfg3 demo cfg2; do
   NB="python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu"
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file "$OUT/launches_$WL.csv" $NB > "$OUT/ncu_list_$WL.log" 2>&1; echo "list $WL rc=$?"
@@ -44,14 +51,17 @@ for WL in cfg5 cfg3; do
   NB="python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu"
   for k in k_jacobi_tb k_preproject k_gradient_mask; do
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 6 -c 1 -o "$OUT/${WL}_$k" -f $NB > "$OUT/ncu_${WL}_$k.log" 2>&1; echo "$WL $k rc=$?"
+    keep "${WL}_$k" $([ $WL = cfg3 ] && echo source)
   done
 done
 for WL in demo cfg2; do
   NB="python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_jacobi_smem -s 6 -c 1 -o "$OUT/${WL}_k_jacobi_smem" -f $NB > "$OUT/ncu_${WL}_smem.log" 2>&1; echo "$WL smem rc=$?"
+  keep "${WL}_k_jacobi_smem" source
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_dye_advect -s 3 -c 1 -o "$OUT/cfg3_k_dye_advect" -f python bench.py --workload cfg3 --steps 2 --warmup 3 --no-cpu > "$OUT/ncu_cfg3_dye.log" 2>&1
+keep cfg3_k_dye_advect
 # ---- per-tile trace of one Jacobi launch (idle / imbalance analysis)
 NATRIX_TB_TRACE=$OUT/tb_trace_cfg3.csv timeout 200 python bench.py --workload cfg3 --steps 3 --warmup 3 --no-cpu > /dev/null 2>&1
 NATRIX_TB_TRACE=$OUT/tb_trace_cfg5.csv timeout 200 python bench.py --workload cfg5 --steps 3 --warmup 3 --no-cpu > /dev/null 2>&1
-ls -la "$OUT" | head -60
+du -sh "$OUT"; ls "$OUT" | wc -l

@@ -129,6 +129,44 @@ def test_temporal_blocking_is_depth_independent(kernel, depth):
     assert_fields_close(out[1], out[0], f"depth {depth}: ", exact=True)
 
 
+@pytest.mark.parametrize("kernel", [TB, SMEM])
+def test_subnormal_divergence_takes_the_two_step_form(kernel):
+    """The temporally blocked kernels read 0.25 * divergence and end a sweep in one fma (common.cuh NB_RAW), which is
+    bit-identical to the shader's (sum - b) * 0.25 except where 0.25 * b is inexact: a non-zero |b| < 2^-124.  Those
+    cells must carry the NB_RAW bit and take the two-step form.  Velocities around 1e-38 in the left half of the grid
+    make such divergences; the right half holds ordinary values, so both forms run side by side in one row."""
+    w, h = 256, 96
+    rng = np.random.default_rng(5)
+    v0 = (0.5 * rng.uniform(-1, 1, (h, w, 2))).astype(np.float32)
+    v0[:, : w // 2] = (rng.integers(-40, 40, (h, w // 2, 2)).astype(np.float64) * 2.0 ** -149 * 7).astype(np.float32)
+    v0[10:30, 20:60] = 0.0
+    outs = []
+    for pipeline, k in ((0, None), (1, kernel)):
+        s = _sim_cls(pipeline, kernel=k)(w, h)
+        s.vorticity, s.viscosity, s.iterations, s.has_borders = 0.0, 0.0, 21, False
+        s.upload("velocity", v0)
+        s.add_circle_obstacle((0.3, 0.5), 12.0)
+        s.update(0.0)                                  # dt = 0: the back-trace returns the cell itself, the tiny values survive
+        outs.append(W.fields_of(s))
+        if pipeline:
+            m, b, b4 = s.download("nbmask"), s.download("divergence"), s.download("div4")
+            raw = (m & 16) != 0
+            assert raw.any() and not raw[:, w // 2 + 2:].any()
+            assert np.array_equal(b4[raw], b[raw]) and np.array_equal(b4[~raw], (b * np.float32(0.25))[~raw])
+            assert np.array_equal((b4 * np.float32(4.0))[~raw], b[~raw])
+            tiny = (b != 0) & (np.abs(b) < 2.0 ** -124)
+            assert tiny.any() and not (raw & ~tiny).any()
+        s.destroy()
+    assert_fields_close(outs[1], outs[0], f"kernel {kernel} vs reference-order pipeline: ", exact=True)
+    o = OracleFluidSimulator(w, h)
+    o.vorticity, o.viscosity, o.iterations, o.has_borders = 0.0, 0.0, 21, False
+    o.velocity = v0
+    o.add_circle_obstacle((0.3, 0.5), 12.0)
+    o.update(0.0)
+    assert_fields_close(outs[1], W.fields_of(o), f"kernel {kernel} vs oracle: ", exact=True)
+    assert float(np.abs(outs[1]["pressure"]).max()) > 0.0
+
+
 @pytest.mark.parametrize("w,h", [(97, 61), (256, 40), (272, 33), (1000, 24), (16, 300), (1, 9), (130, 1)])
 def test_ragged_and_degenerate_sizes_vs_oracle(w, h):
     rng = np.random.default_rng(w + 1000 * h)
