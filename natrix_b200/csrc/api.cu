@@ -702,7 +702,8 @@ int step_slab(natrix_sim* s, float dt) {
         }
         if (i == 0) {
             // p starts at zero, halos included - unless the simulator warm-starts from the last step's pressure
-            const int first[3] = {NATRIX_DIV4, NATRIX_NBMASK, NATRIX_PRESSURE};      // the sweeps read the scaled divergence
+            // the fused pipeline's sweeps read the scaled divergence, the reference-order pipeline the divergence itself
+            const int first[3] = {s->pipeline != 0 ? NATRIX_DIV4 : NATRIX_DIVERGENCE, NATRIX_NBMASK, NATRIX_PRESSURE};
             if (int rc = exchange_fields(s, first, s->warm_start ? 3 : 2, std::min(span, n), xs)) return rc;
         } else {
             if (int rc = exchange_fields(s, &prs, 1, t, xs)) return rc;
