@@ -72,7 +72,13 @@ enum natrix_option {
                                 shared-memory tiles for small, latency-bound grids and for widths TMA cannot
                                 address, register streaming behind TMA otherwise), 1 = TMA kernel, 2 = shared-memory
                                 kernel.  natrix_get_option reports the kernel in use (1 or 2; 0 under pipeline 0) */
-    NATRIX_OPT_SMEM_DEPTH = 6 /* sweeps per launch of the shared-memory Jacobi kernel, 1..16 (default 16)  */
+    NATRIX_OPT_SMEM_DEPTH = 6, /* sweeps per launch of the shared-memory Jacobi kernel, 1..16 (default 16)  */
+    /* Pressure solvers that are NOT reference behaviour (the reference only has the Jacobi loop of
+       fluid_simulator.py:251-255).  Same linear system, full grids only, fused pipeline only; `iterations` then counts
+       red-black SOR sweeps / V-cycles.  Checked bit for bit against oracle/natrix_oracle.py rb_sor_sweep / mg_v_cycle. */
+    NATRIX_OPT_SOLVER = 7,   /* 0 = Jacobi (default, the reference), 1 = red-black SOR, 2 = multigrid V-cycles   */
+    NATRIX_OPT_SOR_OMEGA_MILLI = 8, /* over-relaxation factor x 1000 of solver 1 (default 1900)                     */
+    NATRIX_OPT_MG_SMOOTH = 9 /* red-black Gauss-Seidel sweeps before and after each coarse-grid correction (default 2) */
 };
 
 /* ---- lifetime ------------------------------------------------------------------------

@@ -16,7 +16,8 @@ LIB_PATH = Path(os.environ.get("NATRIX_B200_LIB") or _PKG / "libnatrix_b200.so")
 
 # enum natrix_field / natrix_option (include/natrix_b200.h)
 VELOCITY, PRESSURE, DIVERGENCE, VORTICITY, OBSTACLES, NBMASK, DIV4 = range(7)
-OPT_PIPELINE, OPT_JACOBI_DEPTH, OPT_TIMING, OPT_WARM_START, OPT_PACKED, OPT_JACOBI_KERNEL, OPT_SMEM_DEPTH = range(7)
+(OPT_PIPELINE, OPT_JACOBI_DEPTH, OPT_TIMING, OPT_WARM_START, OPT_PACKED, OPT_JACOBI_KERNEL, OPT_SMEM_DEPTH, OPT_SOLVER,
+ OPT_SOR_OMEGA_MILLI, OPT_MG_SMOOTH) = range(10)
 
 FIELD_COMPONENTS = {VELOCITY: 2, PRESSURE: 1, DIVERGENCE: 1, VORTICITY: 1, OBSTACLES: 2, NBMASK: 1, DIV4: 1}
 

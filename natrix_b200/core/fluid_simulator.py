@@ -254,6 +254,35 @@ class FluidSimulator:
     def warm_start(self, value: bool):
         self.set_option(L.OPT_WARM_START, 1 if value else 0)
 
+    _SOLVERS = ("jacobi", "sor", "multigrid")
+
+    @property
+    def solver(self) -> str:
+        """NOT reference behaviour (default "jacobi", the reference's loop, fluid_simulator.py:251-255): "sor" runs
+        `iterations` red-black SOR sweeps (`sor_omega`), "multigrid" `iterations` V(mg_smooth, mg_smooth) cycles on the same
+        linear system.  Full grids, fused pipeline."""
+        return self._SOLVERS[self.get_option(L.OPT_SOLVER)]
+
+    @solver.setter
+    def solver(self, name: str):
+        self.set_option(L.OPT_SOLVER, self._SOLVERS.index(name))
+
+    @property
+    def sor_omega(self) -> float:
+        return self.get_option(L.OPT_SOR_OMEGA_MILLI) / 1000.0
+
+    @sor_omega.setter
+    def sor_omega(self, value: float):
+        self.set_option(L.OPT_SOR_OMEGA_MILLI, int(round(value * 1000)))
+
+    @property
+    def mg_smooth(self) -> int:
+        return self.get_option(L.OPT_MG_SMOOTH)
+
+    @mg_smooth.setter
+    def mg_smooth(self, value: int):
+        self.set_option(L.OPT_MG_SMOOTH, int(value))
+
     def _shape(self, fid: int):
         comps = L.FIELD_COMPONENTS[fid]
         return (self._rows, self._width, comps) if comps > 1 else (self._rows, self._width)

@@ -114,6 +114,9 @@ struct natrix_sim {
     int iterations = 50, has_borders = 1, viscous = 1;
     // options
     int pipeline = 1, jacobi_depth = 8, timing = 0, packed = 1, warm_start = 0;
+    // solvers that are not reference behaviour (solvers.cu): 0 Jacobi (the reference), 1 red-black SOR, 2 multigrid
+    int solver = 0, sor_omega_milli = 1900, mg_smooth = 2;
+    Multigrid* mg = nullptr;
     int jacobi_kernel = 0;                       // NATRIX_OPT_JACOBI_KERNEL: 0 auto, 1 TMA register streaming, 2 shared memory
     int smem_depth = 0;                          // sweeps per launch of the shared-memory kernel (set at create)
     // bookkeeping
@@ -538,6 +541,27 @@ int phase_jacobi_edges(natrix_sim* s, int sweeps) {
     return 0;
 }
 
+// NATRIX_OPT_SOLVER 1 / 2 in place of the Jacobi sweeps (full grid): `iterations` red-black SOR sweeps or V-cycles on
+// the pressure buffer in place, from zero unless the simulator warm-starts
+int phase_solver(natrix_sim* s) {
+    Range nvtx_range(s->solver == 1 ? "natrix.sor" : "natrix.multigrid");
+    const Geom& g = s->g;
+    if (g.hl != g.hg) return fail(NATRIX_ERR_STATE, "the SOR / multigrid solvers run on a full grid only");
+    float* p = s->p[s->pr];
+    if (s->p_is_zero) CU(cudaMemsetAsync(p, 0, (size_t)g.w * g.hl * sizeof(float), s->st));
+    s->p_is_zero = false;
+    if (s->solver == 1) {
+        for (int k = 0; k < s->iterations; ++k)
+            s->launches += launch_sor_sweep(p, s->div, s->nbm, g.w, g.hl, (float)(s->sor_omega_milli * 1e-3), s->st);
+    } else {
+        if (!s->mg) s->mg = multigrid_create(g.w, g.hl);
+        if (!s->mg) return fail(NATRIX_ERR_CUDA, "multigrid: out of device memory");
+        s->launches += multigrid_solve(s->mg, p, s->div, s->obs, s->nbm, s->iterations, s->mg_smooth, s->st);
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int phase_project(natrix_sim* s) {
     Range nvtx_range("natrix.subtract_gradient");
     const Geom& g = s->g;
@@ -812,6 +836,7 @@ int natrix_destroy(natrix_sim* s) {
     for (natrix_dye* d : s->dyes) d->sim = nullptr;   // orphaned dye handles stay destroyable
     if (s->comm) { nccl()->CommDestroy(s->comm); s->comm = nullptr; }
     jacobi_tb_destroy(s->tb);
+    multigrid_destroy(s->mg);
     for (int i = 0; i < 2; ++i) { cudaFree(s->vel_base[i]); cudaFree(s->p_base[i]); }
     cudaFree(s->div_base); cudaFree(s->vort_base); cudaFree(s->div4_base); cudaFree(s->obs_base); cudaFree(s->nbm_base);
     cudaFree(s->d_err); cudaFree(s->d_scratch); cudaFree(s->d_out4); cudaFree(s->d_tmp2);
@@ -863,6 +888,16 @@ int natrix_set_option(natrix_sim* s, int option, int value) {
     case NATRIX_OPT_TIMING: s->timing = value ? 1 : 0; return 0;
     case NATRIX_OPT_PACKED: s->packed = value ? 1 : 0; return 0;
     case NATRIX_OPT_WARM_START: s->warm_start = value ? 1 : 0; return 0;
+    case NATRIX_OPT_SOLVER:
+        NEED(value >= 0 && value <= 2, "solver must be 0 (Jacobi, the reference), 1 (red-black SOR) or 2 (multigrid)");
+        NEED(value == 0 || s->g.hl == s->g.hg, "the SOR / multigrid solvers run on a full grid only");
+        s->solver = value; return 0;
+    case NATRIX_OPT_SOR_OMEGA_MILLI:
+        NEED(value > 0 && value < 2000, "SOR omega (x 1000) must lie in (0, 2000)");
+        s->sor_omega_milli = value; return 0;
+    case NATRIX_OPT_MG_SMOOTH:
+        NEED(value >= 1 && value <= 8, "multigrid smoothing sweeps must lie in 1..8");
+        s->mg_smooth = value; return 0;
     case NATRIX_OPT_JACOBI_KERNEL:
         NEED(value >= 0 && value <= 2, "jacobi kernel must be 0 (auto), 1 (TMA register streaming) or 2 (shared memory)");
         NEED(value != 1 || jacobi_tb_supported(s->g), "the TMA kernel needs width % 16 == 0 and width >= 128");
@@ -884,6 +919,9 @@ int natrix_get_option(natrix_sim* s, int option, int* value) {
     case NATRIX_OPT_WARM_START: *value = s->warm_start; return 0;
     case NATRIX_OPT_JACOBI_KERNEL: *value = s->pipeline == 0 ? 0 : (use_smem_kernel(s) ? 2 : 1); return 0;   // the one in use
     case NATRIX_OPT_SMEM_DEPTH: *value = s->smem_depth; return 0;
+    case NATRIX_OPT_SOLVER: *value = s->solver; return 0;
+    case NATRIX_OPT_SOR_OMEGA_MILLI: *value = s->sor_omega_milli; return 0;
+    case NATRIX_OPT_MG_SMOOTH: *value = s->mg_smooth; return 0;
     default: return fail(NATRIX_ERR_ARG, "unknown option id");
     }
 }
@@ -1051,7 +1089,7 @@ int natrix_step(natrix_sim* s, float dt) {
     if (int rc = phase_advect(s, dt)) return rc;
     if (int rc = phase_forces(s, dt)) return rc;
     stamp(s, ST_JACOBI);
-    if (int rc = phase_jacobi(s, s->iterations)) return rc;
+    if (int rc = s->solver != 0 && s->pipeline != 0 ? phase_solver(s) : phase_jacobi(s, s->iterations)) return rc;
     if (int rc = phase_project(s)) return rc;
     return 0;
 }

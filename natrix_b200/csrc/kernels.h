@@ -87,4 +87,16 @@ int launch_splat_dye_boxes(float* dye, Geom dg, int r0, int r1, const SplatD* sp
 // n queued circles (sx, sy, radius triples, in cells) rasterised on their bounding boxes, rows [r0, r1)
 int launch_add_circles(uint8_t* obs, Geom g, int r0, int r1, const float* sxyr, int n, cudaStream_t st);
 
+// ---- opt-in solvers that are not reference behaviour (solvers.cu); full grids only
+// one red-black SOR sweep (both colours) in place on p; returns the kernels launched
+int launch_sor_sweep(float* p, const float* rhs, const uint8_t* mask, int w, int h, float omega, cudaStream_t st);
+struct Multigrid;
+Multigrid* multigrid_create(int w, int h);        // nullptr when device memory ran out
+void multigrid_destroy(Multigrid* mg);
+int multigrid_levels(const Multigrid* mg);
+// `cycles` V(nu, nu) cycles with a red-black Gauss-Seidel smoother on the full grid's (p, rhs); obs / mask are the
+// step's obstacle bytes and blocked-neighbour mask.  Returns the kernels launched.
+int multigrid_solve(Multigrid* mg, float* p, const float* rhs, const uint8_t* obs, const uint8_t* mask, int cycles, int nu,
+                    cudaStream_t st);
+
 }  // namespace natrix

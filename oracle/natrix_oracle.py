@@ -397,6 +397,73 @@ def render_frame(dye, vel=None, quiver_tile=0.0):
 
 
 # ------------------------------------------------------------------ simulator mirror
+# ---------------------------------------------------------------------------------------------------------------
+# Pressure solvers that are NOT reference behaviour (product: natrix_b200/csrc/solvers.cu, opt-in
+# through NATRIX_OPT_SOLVER).  They solve the same system as shader.Poisson.comp:24-37 iterates on -
+# x1 + x2 + y1 + y2 - 4 p = div with the centre substituted for solid / outside neighbours - and are restated here
+# operation by operation so that the CUDA kernels can be checked bit for bit.
+def rb_sor_sweep(p, rhs, nb, omega):
+    """One red-black successive over-relaxation sweep: cells with (x + y) even, then the others, each
+    p <- p + omega * (gs - p) with gs the shader's Jacobi update of that cell from the CURRENT field."""
+    h, w = p.shape
+    yy, xx = np.mgrid[0:h, 0:w]
+    red = ((xx + yy) & 1) == 0
+    for colour in (red, ~red):
+        gs = poisson_sweep(p, rhs, None, nb)
+        p = np.where(colour, p + F(omega) * (gs - p), p)
+    return p
+
+
+def mg_restrict(a):
+    """full weighting of a cell-centred grid: the mean of the 2 x 2 children"""
+    return F(0.25) * (a[0::2, 0::2] + a[1::2, 0::2] + a[0::2, 1::2] + a[1::2, 1::2])
+
+
+def mg_prolong(a):
+    """cell-centred bilinear interpolation (weights 9/16, 3/16, 3/16, 1/16), clamp-to-edge; rows first, then columns"""
+    def up(x, axis):
+        lo = np.concatenate([np.take(x, [0], axis), np.take(x, range(x.shape[axis] - 1), axis)], axis)
+        hi = np.concatenate([np.take(x, range(1, x.shape[axis]), axis), np.take(x, [-1], axis)], axis)
+        even, odd = F(0.75) * x + F(0.25) * lo, F(0.75) * x + F(0.25) * hi
+        out = np.stack([even, odd], axis=axis + 1)
+        shape = list(x.shape)
+        shape[axis] *= 2
+        return out.reshape(shape)
+    return up(up(a, 0), 1)
+
+
+def mg_levels(solid0, min_size=16):
+    """solid maps of the multigrid hierarchy: a coarse cell is solid when all four children are; coarsening stops
+    when a side is odd or the next level would be smaller than min_size / 2 on a side"""
+    solids = [solid0]
+    while min(solids[-1].shape) >= min_size and solids[-1].shape[0] % 2 == 0 and solids[-1].shape[1] % 2 == 0:
+        s = solids[-1]
+        solids.append(s[0::2, 0::2] & s[1::2, 0::2] & s[0::2, 1::2] & s[1::2, 1::2])
+    return solids
+
+
+def mg_v_cycle(p, rhs, solids, level, nu):
+    """One V(nu, nu) cycle with a red-black Gauss-Seidel smoother.  rhs plays the role of `div` at this level."""
+    nb = neighbours(solids[level])
+    for _ in range(nu):
+        p = rb_sor_sweep(p, rhs, nb, 1.0)
+    if level + 1 < len(solids):
+        # residual of x1 + x2 + y1 + y2 - 4 p = rhs with the same neighbour substitution
+        pl, pr, pb, pt = neighbours(p)
+        sl, sr, sb, st = nb
+        lap = np.where(sl, p, pl) + np.where(sr, p, pr) + np.where(sb, p, pb) + np.where(st, p, pt) - F(4.0) * p
+        # solid cells carry no equation (their own update only ever sees themselves): whatever divergence the
+        # stencil left in them must not reach the coarse grid, where it would be "corrected" again every cycle
+        # (without this line the iteration diverges on deep hierarchies: 1024^2 with one circle, 8 levels)
+        r = np.where(solids[level], F(0.0), rhs - lap)
+        coarse_rhs = F(4.0) * mg_restrict(r)                     # h -> 2h: the right-hand side scales by 4
+        e = mg_v_cycle(np.zeros_like(coarse_rhs), coarse_rhs, solids, level + 1, nu)
+        p = p + mg_prolong(e)
+    for _ in range(nu):
+        p = rb_sor_sweep(p, rhs, nb, 1.0)
+    return p
+
+
 class OracleFluidSimulator:
     """State machine of natrix/core/fluid_simulator.py:15-515 over NumPy arrays.
 
@@ -479,10 +546,19 @@ class OracleFluidSimulator:
         if not getattr(self, "warm_start", False):      # warm_start: opt-in extension of the product, not the reference
             self._p[self.PRESSURE_READ] = np.zeros_like(self._p[0])             # :236-248
         nb = neighbours(solid(self.obstacles))
-        for _ in range(int(self.iterations)):                                   # :251-255
-            self._p[self.PRESSURE_WRITE] = poisson_sweep(
-                self.pressure, self.divergence, self.obstacles, nb)
-            self._flip_p()
+        solver = getattr(self, "solver", "jacobi")      # "sor" / "multigrid": opt-in extensions of the product
+        if solver == "sor":
+            for _ in range(int(self.iterations)):
+                self._p[self.PRESSURE_READ] = rb_sor_sweep(self.pressure, self.divergence, nb, getattr(self, "sor_omega", 1.9))
+        elif solver == "multigrid":
+            solids = mg_levels(solid(self.obstacles))
+            for _ in range(int(self.iterations)):
+                self._p[self.PRESSURE_READ] = mg_v_cycle(self.pressure, self.divergence, solids, 0, int(getattr(self, "mg_smooth", 2)))
+        else:
+            for _ in range(int(self.iterations)):                               # :251-255
+                self._p[self.PRESSURE_WRITE] = poisson_sweep(
+                    self.pressure, self.divergence, self.obstacles, nb)
+                self._flip_p()
         self._vel[self.VELOCITY_WRITE] = subtract_gradient(
             self.velocity, self.pressure, self.obstacles)                       # :258-265
         self._flip_v()

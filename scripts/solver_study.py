@@ -45,46 +45,8 @@ def jacobi(p, div, nb, sweeps):
 
 
 def rb_sor(p, div, nb, sweeps, omega):
-    h, w = p.shape
-    yy, xx = np.mgrid[0:h, 0:w]
-    red = ((xx + yy) & 1) == 0
     for _ in range(sweeps):
-        for colour in (red, ~red):
-            gs = O.poisson_sweep(p, div, None, nb)
-            p = np.where(colour, p + F(omega) * (gs - p), p)
-    return p
-
-
-def restrict(a):
-    return F(0.25) * (a[0::2, 0::2] + a[1::2, 0::2] + a[0::2, 1::2] + a[1::2, 1::2])
-
-
-def prolong(a):
-    """cell-centred bilinear interpolation (weights 9/16, 3/16, 3/16, 1/16), clamp-to-edge"""
-    def up(x, axis):
-        lo = np.concatenate([np.take(x, [0], axis), np.take(x, range(x.shape[axis] - 1), axis)], axis)
-        hi = np.concatenate([np.take(x, range(1, x.shape[axis]), axis), np.take(x, [-1], axis)], axis)
-        even, odd = F(0.75) * x + F(0.25) * lo, F(0.75) * x + F(0.25) * hi
-        out = np.stack([even, odd], axis=axis + 1)
-        shape = list(x.shape)
-        shape[axis] *= 2
-        return out.reshape(shape)
-    return up(up(a, 0), 1)
-
-
-def v_cycle(p, rhs, solids, level, nu, work):
-    """rhs plays the role of `div` of shader.Poisson.comp at this level; solids[level] is the coarsened obstacle map."""
-    nb = O.neighbours(solids[level])
-    p = rb_sor(p, rhs, nb, nu, 1.0)
-    work[0] += nu * 4.0 ** -level
-    if level + 1 < len(solids) and min(p.shape) >= 8:
-        # residual of  (x1 + x2 + y1 + y2 - 4 p) = rhs  with the same neighbour substitution
-        r = rhs - (O.poisson_sweep(p, np.zeros_like(p), None, nb) * F(4.0) - F(4.0) * p)
-        e = v_cycle(np.zeros_like(restrict(r)), F(4.0) * restrict(r), solids, level + 1, nu, work)   # h -> 2h: rhs scales by 4
-        p = p + prolong(e)
-        work[0] += 0.5 * 4.0 ** -level
-    p = rb_sor(p, rhs, nb, nu, 1.0)
-    work[0] += nu * 4.0 ** -level
+        p = O.rb_sor_sweep(p, div, nb, omega)
     return p
 
 
@@ -101,16 +63,13 @@ def main():
     for omega in (1.0, 1.7, 1.9):
         for s in (25, 50, 100):
             print(f"{f'red-black SOR, omega = {omega}':34s} {s:8d} {residual(vel, rb_sor(zero, div, nb, s, omega), obs):15.3e}")
-    solids = [O.solid(obs)]
-    while min(solids[-1].shape) >= 16:
-        s = solids[-1]
-        solids.append(s[0::2, 0::2] & s[1::2, 0::2] & s[0::2, 1::2] & s[1::2, 1::2])      # coarse cell solid if all four are
+    solids = O.mg_levels(O.solid(obs))
+    per_cycle = sum((2 * 2 + 0.5) * 4.0 ** -lv for lv in range(len(solids)))          # fine-grid passes of one V(2,2)
     for cycles in (1, 2, 4, 8):
-        work = [0.0]
         p = zero
         for _ in range(cycles):
-            p = v_cycle(p, div, solids, 0, 2, work)
-        print(f"{f'V(2,2) x {cycles}, red-black smoother':34s} {work[0]:8.1f} {residual(vel, p, obs):15.3e}")
+            p = O.mg_v_cycle(p, div, solids, 0, 2)
+        print(f"{f'V(2,2) x {cycles}, red-black smoother':34s} {cycles * per_cycle:8.1f} {residual(vel, p, obs):15.3e}")
 
 
 if __name__ == "__main__":

@@ -497,6 +497,64 @@ def test_warm_start_option_vs_oracle(pipeline, kernel):
     assert not np.array_equal(g.download("pressure"), cold.download("pressure"))
 
 
+@pytest.mark.parametrize("solver,iters,size", [("sor", 30, (256, 160)), ("multigrid", 3, (256, 160)), ("multigrid", 2, (130, 66)),
+                                               ("sor", 7, (97, 61)), ("multigrid", 2, (512, 512))])
+def test_solver_extensions_vs_oracle(solver, iters, size):
+    """SURVEY 8(f)-4 (NOT reference behaviour): red-black SOR and multigrid V-cycles behind NATRIX_OPT_SOLVER solve the
+    system the reference's Jacobi loop iterates on; every field bit-identical to the NumPy restatement
+    (oracle rb_sor_sweep / mg_v_cycle), on grids with 5, 2 (odd coarse side), 1 and 6 levels."""
+    from oracle.natrix_oracle import OracleFluidSimulator as NumpyOracle     # the reference's shaders have no such solver
+
+    w, h = size
+    v0 = W.random_velocity(w, h, seed=21)
+    g, o = FluidSimulator(w, h), NumpyOracle(w, h)
+    g.solver = solver
+    o.solver = solver
+    assert g.solver == solver
+    for s in (g, o):
+        s.vorticity, s.viscosity, s.iterations = 1.5, 0.0, iters
+    if solver == "sor":
+        g.sor_omega = o.sor_omega = 1.7
+    else:
+        g.mg_smooth = o.mg_smooth = 2
+    g.upload("velocity", v0)
+    o.velocity = v0
+    for k in range(3):
+        for s in (g, o):
+            s.add_circle_obstacle((0.35, 0.55), min(w, h) / 6.0)
+            s.add_triangle_obstacle((0.6, 0.2), (0.9, 0.3), (0.7, 0.8))
+            s.update(W.DT)
+            s.add_velocity((0.5, 0.5), (0.6, -0.3), 9.0)
+        assert_fields_close(W.fields_of(g), W.fields_of(o), f"{solver} {w}x{h} step {k}: ", exact=True)
+    g.destroy()
+
+
+def test_solver_extensions_leave_less_residual_than_jacobi_for_the_time():
+    """what the extensions are for: the RMS residual of the pressure system after one solve, against the solve's
+    device time - 3 V(2,2) cycles beat 200 Jacobi sweeps on a 1024^2 grid with obstacles"""
+    from oracle import natrix_oracle as O
+
+    w = W.cfg2_workload()
+    out = {}
+    for name, solver, iters in (("jacobi", "jacobi", 200), ("multigrid", "multigrid", 3)):
+        s, _ = W.build(w, FluidSimulator, None)
+        s.solver, s.iterations = solver, iters
+        s.set_option(L.OPT_TIMING, 1)
+        for k in range(2):
+            for (px, py, r) in w.circles:
+                s.add_circle_obstacle((px, py), r)
+            obstacles = s.download("obstacles")
+            s.update(W.DT)
+        p, div = s.download("pressure"), s.download("divergence")
+        nb = O.neighbours(O.solid(obstacles))
+        r = O.poisson_sweep(p, div, None, nb) * np.float32(4.0) - np.float32(4.0) * p
+        fluid = ~O.solid(obstacles)
+        out[name] = (float(np.sqrt(np.mean(r[fluid].astype(np.float64) ** 2))), s.timings()["jacobi"])
+        s.destroy()
+    assert out["multigrid"][0] < out["jacobi"][0], out
+    print("residual, ms:", out)
+
+
 def test_checkpoint_restores_a_run_bit_identically(tmp_path):
     """natrix_b200.checkpoint through the C ABI: velocity, pressure, pending obstacles, parameters and the dye."""
     from natrix_b200 import checkpoint
