@@ -119,6 +119,10 @@ struct natrix_sim {
     Multigrid* mg = nullptr;
     int jacobi_kernel = 0;                       // NATRIX_OPT_JACOBI_KERNEL: 0 auto, 1 TMA register streaming, 2 shared memory
     int smem_depth = 0;                          // sweeps per launch of the shared-memory kernel (set at create)
+    // gradient subtraction as the epilogue of the step's last shared-memory Jacobi launch (full grids; NATRIX_SMEM_GRAD=0
+    // turns it off): natrix_step asks for it, phase_jacobi does it, phase_project then skips its own launch
+    int smem_grad = 1;
+    bool grad_wanted = false, grad_done = false;
     // bookkeeping
     std::vector<SplatV> pending;                 // add_velocity calls not yet applied (pipeline 1)
     std::vector<float> circles;                  // queued add_circle_obstacle calls (sx, sy, r), pipeline 1
@@ -199,7 +203,7 @@ void mark_heavy_rows(natrix_sim* s, double glo, double ghi, double xlo = -1e30, 
     const int by0 = std::max((int)std::floor(std::max(glo, -1e9)) - margin - s->g.y0, -s->g.halo);
     const int by1 = std::min((int)std::ceil(std::min(ghi, 1e9)) + margin + 1 - s->g.y0, s->g.hl + s->g.halo);
     if (by1 <= by0) return;                          // does not touch the rows this slab holds
-    if (circle && s->boxes.size() < 4 * 256) {
+    if (circle && 0.5 * (ghi - glo) < 1e6 && s->boxes.size() < 4 * 256) {
         // a circle keeps its geometry: (cx, -1 - r, cy local, 0), see jacobi_tb.h
         const double r = 0.5 * (ghi - glo);
         s->boxes.insert(s->boxes.end(), {(int)std::lround(0.5 * (xlo + xhi)), -1 - (int)std::ceil(r),
@@ -214,7 +218,8 @@ void mark_heavy_rows(natrix_sim* s, double glo, double ghi, double xlo = -1e30, 
             }
         }
     }
-    int lo = (int)std::floor(glo) - margin - s->g.y0, hi = (int)std::ceil(ghi) + margin + 1 - s->g.y0;
+    // (clamped in double first: a radius beyond 2^31 must not overflow the casts)
+    int lo = (int)std::floor(std::max(glo, -1e9)) - margin - s->g.y0, hi = (int)std::ceil(std::min(ghi, 1e9)) + margin + 1 - s->g.y0;
     lo = std::max(lo, -s->g.halo);
     hi = std::min(hi, s->g.hl + s->g.halo);
     if (hi <= lo) return;
@@ -420,14 +425,16 @@ int jacobi_launch_depth(const natrix_sim* s) {
 
 // `sweeps` Jacobi sweeps; requires p, div, nbmask valid on ext(sweeps) (exchange done by caller)
 // One launch of `depth` Jacobi sweeps over local rows [r0, r1): p[src] -> p[1 - src] on stream st.
-int jacobi_rows(natrix_sim* s, int src, int depth, int r0, int r1, bool p_zero, cudaStream_t st) {
+int jacobi_rows(natrix_sim* s, int src, int depth, int r0, int r1, bool p_zero, cudaStream_t st, bool with_gradient = false) {
     if (r1 <= r0) return 0;
     const Geom& g = s->g;
     if (s->pipeline == 0) {
         s->launches += launch_poisson_ref(s->p[src], s->div, s->obs, s->p[1 - src], g, r0, r1, st);
     } else if (use_smem_kernel(s)) {
         // small grids (latency-bound) and widths TMA cannot address: one tile per block in shared memory
-        const int n = launch_jacobi_smem(s->p[src], s->div4, s->nbm, s->p[1 - src], g, depth, r0, r1, p_zero, s->sm_count, st);
+        const int n = launch_jacobi_smem(s->p[src], s->div4, s->nbm, s->p[1 - src], g, depth, r0, r1, p_zero, s->sm_count, st,
+                                         with_gradient ? s->vel[s->vr] : nullptr, with_gradient ? s->vel[1 - s->vr] : nullptr,
+                                         s->d_err + 1);
         if (n < 0) return fail(NATRIX_ERR_CUDA, std::string("k_jacobi_smem launch: ") + cudaGetErrorString(cudaGetLastError()));
         s->launches += n;
     } else {
@@ -449,7 +456,10 @@ int phase_jacobi(natrix_sim* s, int sweeps) {
             const int launches = (left + t - 1) / t;
             t = (left + launches - 1) / launches;
         }
-        if (int rc = jacobi_rows(s, s->pr, t, s->ext_lo(left - t), s->ext_hi(left - t), s->p_is_zero, s->st)) return rc;
+        // the launch with the step's last sweeps takes the gradient subtraction along (shared-memory kernel, full grid)
+        const bool grad = s->grad_wanted && left == t && use_smem_kernel(s) && s->g.hl == s->g.hg;
+        if (int rc = jacobi_rows(s, s->pr, t, s->ext_lo(left - t), s->ext_hi(left - t), s->p_is_zero, s->st, grad)) return rc;
+        if (grad) s->grad_done = true;
         s->pr = 1 - s->pr;
         left -= t;
         s->p_is_zero = false;
@@ -566,7 +576,9 @@ int phase_project(natrix_sim* s) {
     Range nvtx_range("natrix.subtract_gradient");
     const Geom& g = s->g;
     stamp(s, ST_GRAD);
-    if (s->pipeline == 0)
+    if (s->grad_done)
+        s->grad_done = false;                    // the last Jacobi launch wrote the projected velocity already
+    else if (s->pipeline == 0)
         s->launches += launch_gradient_ref(s->vel[s->vr], s->p[s->pr], s->obs, s->vel[1 - s->vr], g, 0, g.hl, s->st);
     else
         s->launches += launch_gradient_mask(s->vel[s->vr], s->p[s->pr], s->nbm, s->vel[1 - s->vr], g, 0, g.hl,
@@ -821,6 +833,7 @@ int natrix_create_slab(int width, int global_height, int row0, int rows, int hal
     }
     s->tb = jacobi_tb_create();
     s->smem_depth = jacobi_smem_max_depth();
+    if (const char* e = getenv("NATRIX_SMEM_GRAD")) s->smem_grad = atoi(e) != 0;
     *out = s;
     return 0;
 }
@@ -972,7 +985,13 @@ int natrix_add_triangle_obstacle(natrix_sim* s, float p1x, float p1y, float p2x,
         // a degenerate triangle selects whole lines of cells (see stages_ref.cu): call every row heavy
         const double xs[3] = {(double)p1x * g.w, (double)p2x * g.w, (double)p3x * g.w};
         const double xmin = std::min(xs[0], std::min(xs[1], xs[2])), xmax = std::max(xs[0], std::max(xs[1], xs[2]));
-        if (ymax - ymin < 1.0 || xmax - xmin < 1.0) mark_heavy_rows(s, 0.0, (double)g.hg);
+        // ... and so does any (nearly) collinear triple, whatever its bounding box: all three edge functions vanish
+        // along the whole line through the points.  Non-finite vertices select unpredictably: every row as well.
+        const double cross = std::fabs((xs[1] - xs[0]) * (ys[2] - ys[0]) - (xs[2] - xs[0]) * (ys[1] - ys[0]));
+        const double extent = std::max(xmax - xmin, ymax - ymin);
+        const bool finite = std::isfinite(xmin) && std::isfinite(xmax) && std::isfinite(ymin) && std::isfinite(ymax);
+        if (!finite || ymax - ymin < 1.0 || xmax - xmin < 1.0 || cross < 1e-3 * extent * extent + 1.0)
+            mark_heavy_rows(s, 0.0, (double)g.hg);
         else mark_heavy_rows(s, ymin, ymax, xmin, xmax);
     }
     s->obs_dirty = true;
@@ -1089,7 +1108,10 @@ int natrix_step(natrix_sim* s, float dt) {
     if (int rc = phase_advect(s, dt)) return rc;
     if (int rc = phase_forces(s, dt)) return rc;
     stamp(s, ST_JACOBI);
-    if (int rc = s->solver != 0 && s->pipeline != 0 ? phase_solver(s) : phase_jacobi(s, s->iterations)) return rc;
+    s->grad_wanted = s->smem_grad != 0;          // this call runs ALL the step's sweeps: the last launch may project too
+    const int rc_solve = s->solver != 0 && s->pipeline != 0 ? phase_solver(s) : phase_jacobi(s, s->iterations);
+    s->grad_wanted = false;
+    if (rc_solve) return rc_solve;
     if (int rc = phase_project(s)) return rc;
     return 0;
 }

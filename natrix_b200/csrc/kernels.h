@@ -66,8 +66,11 @@ int launch_render_frame(const float* dye, const float4* lut, const float2* vel, 
 // ---- fused pipeline (fused.cu / jacobi_tb.cu) ----------------------------------------------------
 // `depth` (1..16) sweeps pin -> pout for rows [r0, r1), one tile per block in shared memory (jacobi_smem.cu): any
 // width, meant for small grids.  Same contract as jacobi_tb_launch; returns launches, or -1 on a launch error.
+// grad_vin != null: the launch also subtracts the gradient of its result from grad_vin into grad_vout for the same
+// rows (shader.SubtractGradient.comp:24-46) and records |v| > 1 per band in over1 - for the launch with the step's last sweeps.
 int launch_jacobi_smem(const float* pin, const float* div4, const uint8_t* nbmask, float* pout, Geom g, int depth,
-                       int r0, int r1, bool p_is_zero, int sm_count, cudaStream_t st);
+                       int r0, int r1, bool p_is_zero, int sm_count, cudaStream_t st, const float2* grad_vin = nullptr,
+                       float2* grad_vout = nullptr, int* over1 = nullptr);
 int jacobi_smem_max_depth();             // default sweeps per launch (NATRIX_SMEM_DEPTH, <= 16)
 size_t jacobi_smem_cell_limit();         // grids up to this many cells prefer the shared-memory kernel
 // over1: one device int per band of OVER_BAND allocated rows, set when some |v| > 1 is written there

@@ -229,6 +229,26 @@ def test_impulses_and_obstacles_vs_oracle():
     assert_fields_close(W.fields_of(g), W.fields_of(o), exact=True)
 
 
+def test_collinear_triangle_is_cleared_like_any_other_obstacle():
+    """an oblique collinear triangle selects the whole line through its points (all three edge functions vanish there),
+    far outside its bounding box; the fused pipeline clears only the rows it believes were stamped, so it must believe
+    every row was (the reference clears every cell each step)"""
+    w, h = 256, 192
+    g, o = FluidSimulator(w, h), OracleFluidSimulator(w, h)
+    v0 = W.random_velocity(w, h, seed=5)
+    g.upload("velocity", v0)
+    o.velocity = v0
+    for k in range(2):
+        for s in (g, o):
+            s.add_triangle_obstacle((0.25, 0.25), (0.5, 0.5), (0.75, 0.75))
+            s.add_circle_obstacle((0.5, 0.2), 1e10)                 # a radius far beyond 2^31 cells
+        assert np.array_equal(g.download("obstacles"), o.obstacles)
+        for s in (g, o):
+            s.update(W.DT)
+        assert not g.download("obstacles").any()
+        assert_fields_close(W.fields_of(g), W.fields_of(o), f"step {k}: ", exact=True)
+
+
 def test_simulate_false_gates_every_mutator():
     g = FluidSimulator(64, 64)
     v0 = W.random_velocity(64, 64, 1)
