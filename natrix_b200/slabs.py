@@ -496,6 +496,7 @@ def run_bench(args, w, metric, jacobi_bytes, measured_peak_gbs, ClockSampler):
     step = 0
     for _ in range(max(args.warmup, 3)):
         one_step(step); step += 1
+    sim.stats("velocity")        # warm-up covers the e2e leg's readback kernel too (CUDA loads a kernel on its first launch)
     sim.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:

@@ -7,18 +7,12 @@ OUT=gpurun_out/$TAG; mkdir -p "$OUT"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > "$OUT/gpu.txt" 2>&1
 timeout 1500 python -m pytest tests -m gpu -q -x --durations=10 > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?"; tail -4 "$OUT/pytest_gpu.log"
 timeout 600 python bench.py --steps 20 --warmup 3 > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench rc=$?"; tail -3 "$OUT/bench.err"
-B="python bench.py --no-cpu --steps 50 --warmup 5"
+B="python bench.py --no-cpu --steps 100 --warmup 5"
 for WL in demo cfg2; do
+  timeout 200 $B --workload $WL > "$OUT/bench_${WL}.json" 2>> "$OUT/bench.err"
   timeout 200 $B --workload $WL --jacobi-kernel 1 > "$OUT/bench_${WL}_tb.json" 2>> "$OUT/bench.err"
-  for D in 8 12 16; do
-    timeout 200 $B --workload $WL --jacobi-kernel 2 --smem-depth $D > "$OUT/bench_${WL}_smem$D.json" 2>> "$OUT/bench.err"
-  done
 done
-for S in 1536 2048 3072; do
-  for K in 1 2; do
-    timeout 200 python bench.py --no-cpu --steps 10 --warmup 3 --workload cfg4 --size $S --jacobi-kernel $K > "$OUT/bench_cfg4_${S}_k$K.json" 2>> "$OUT/bench.err"
-  done
-done
+timeout 200 python bench.py --no-cpu --steps 20 --warmup 3 --workload cfg3 --pipeline 0 > "$OUT/bench_cfg3_pipeline0.json" 2>> "$OUT/bench.err"
 python - "$OUT" <<'PY'
 import glob, json, sys
 for f in sorted(glob.glob(sys.argv[1] + "/bench*.json")):
@@ -46,6 +40,7 @@ keep() {   # keep <name> [source]
 for WL in cfg5 cfg3 demo cfg2; do
   NB="python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu"
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file "$OUT/launches_$WL.csv" $NB > "$OUT/ncu_list_$WL.log" 2>&1; echo "list $WL rc=$?"
+  python scripts/launch_summary.py "$OUT/launches_$WL.csv" > "$OUT/launches_${WL}_summary.txt" 2>&1
 done
 for WL in cfg5 cfg3; do
   NB="python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu"

@@ -2,7 +2,7 @@
 (dram__bytes_read.sum + dram__bytes_write.sum), its duration, issue-slot utilisation and SM active / elapsed.
 bench.py scales the per-cell figure of the capture nearest in size to the workload it runs.
 
-usage: python scripts/kernel_traffic.py <tag> <report.ncu-rep>:<cells> [...]   (cells = grid cells the launch covered)
+usage: python scripts/kernel_traffic.py <tag> <report.ncu-rep | report.raw.csv>:<cells> [...]   (cells = grid cells the launch covered)
 """
 import csv
 import io
@@ -29,7 +29,9 @@ def main():
     for arg in sys.argv[2:]:
         path, cells = arg.rsplit(":", 1)
         cells = int(cells)
-        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        # a report, or the `ncu -i <report> --page raw --csv` text the GPU session kept in its place
+        raw = open(path).read() if path.endswith(".csv") else \
+            subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         hdr, units = rows[0], rows[1]
         col = {k: i for i, k in enumerate(hdr)}
@@ -42,7 +44,7 @@ def main():
             name = r[col["Kernel Name"]].split("(")[0].replace("void ", "")
             name = name.split("::")[-1]
             caps.append({
-                "kernel": name, "cells": cells, "source": f"profiles/{tag}_{Path(path).stem}_ncu_full.txt (ncu --set full, {Path(path).name})",
+                "kernel": name, "cells": cells, "source": f"profiles/{tag}_{Path(path).name.split('.')[0]}_ncu_details.txt (ncu --set full --clock-control none)",
                 "dram_read_bytes": rd, "dram_write_bytes": wr, "dram_bytes_per_cell_per_launch": (rd + wr) / cells,
                 "duration_us_under_ncu": dur, "grid": val("launch__grid_size"), "block": val("launch__block_size"),
                 "registers": val("launch__registers_per_thread"),
