@@ -10,6 +10,7 @@
 //
 // All of them produce bit-identical results to the one-kernel-per-shader versions in
 // stages_ref.cu (same expressions, same operand order, -fmad=false).
+#include <algorithm>
 #include <type_traits>
 
 #include "kernels.h"
@@ -96,7 +97,7 @@ __device__ __forceinline__ float2 gather_finish(const Gather& q, float diss) {
 // InitBoundaries (shader.InitBoundaries.comp:14-34) is NOT folded in here: when has_borders is set the
 // border lines of the READ buffer are zeroed in place by k_zero_borders first, exactly like the
 // reference's dispatch does (2 (W + H) cells; cheaper than testing every gathered corner).
-// Both variants run 12 warps x 1 CTA per SM (up to 168 registers).
+// Both variants run up to 12 warps per block, one block per SM (up to 168 registers); small grids get smaller blocks.
 // PIPE = false: the gathers of a row are consumed in the same iteration (small grids: shorter warm-up per tile).
 // PIPE = true : the gathers of row ly+1 are issued before the vorticity / confinement / divergence arithmetic
 //               of row ly and consumed one iteration later; the rolling windows rotate without register moves.
@@ -615,9 +616,14 @@ int launch_preproject(const float2* vin, const uint8_t* obs, float2* vout, float
     prm.ch = ch;
     nchunks = (rows + ch - 1) / ch;
     prm.ntiles = prm.nstrips * nchunks;
-    const int blocks = (prm.ntiles + warps - 1) / warps;
+    // a small grid has fewer tiles than the GPU has resident warps (640 x 360: 540): spread them over all the SMs
+    // in smaller blocks instead of filling a third of the SMs with 12 warps each - every tile is one dependent
+    // chain of rows, and a warp that shares its scheduler with two others walks it more slowly
+    // (rounded up: never more blocks than SMs, the kernel runs one block per SM)
+    const int bw = std::max(2, std::min(warps, (prm.ntiles + sm_count - 1) / sm_count));
+    const int blocks = (prm.ntiles + bw - 1) / bw;
     const bool slab = g.hl != g.hg;
-#define NATRIX_PRE(V, S, P) k_preproject<V, S, P><<<blocks, warps * 32, 0, st>>>(vin, obs, vout, vort, div, div4, nbmask, g, prm, err)
+#define NATRIX_PRE(V, S, P) k_preproject<V, S, P><<<blocks, bw * 32, 0, st>>>(vin, obs, vout, vort, div, div4, nbmask, g, prm, err)
     if (pipe) {
         if (viscous) { if (slab) NATRIX_PRE(true, true, true); else NATRIX_PRE(true, false, true); }
         else { if (slab) NATRIX_PRE(false, true, true); else NATRIX_PRE(false, false, true); }

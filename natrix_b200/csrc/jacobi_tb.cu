@@ -633,7 +633,7 @@ struct JacobiTB {
     double sigma = 1.0;
     // measured (ncu, 32768x4096): 256 B promotion fetches 7 % more DRAM bytes than 128 B / none for the same time
     int l2_promotion = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;      // NATRIX_TB_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B
-    double kappa = 2.3;           // measured: 32768x4096, 64 circles, 200 sweeps: 2.0 -> 11.5 ms, 2.3 -> 11.1 ms, 3.0 -> 12.2 ms (8.6 ms without obstacles)
+    double kappa = 2.6;           // measured (this build, 200 sweeps at 32768x4096 with 64 circles / 100 at 4096^2): 2.0 -> 9.95 / 0.684 ms, 2.3 -> 9.91 / 0.661, 2.6 -> 9.65 / 0.662, 3.0 -> 9.56 / 0.682
 
     static constexpr int PU = 4;  // planning granularity (rows) = one TMA group
 
@@ -781,7 +781,7 @@ struct JacobiTB {
         }
         // 3. order = placement: tile i runs on warp i % warps of block i / warps.  Neighbouring warps should stream
         //    neighbouring strips of the same rows, and the warps of one SM share its issue slots, so the tiles with
-        //    select-body rows (2.3x the instructions) are dealt out over the blocks instead of sitting together
+        //    select-body rows (2 - 3x the instructions) are dealt out over the blocks instead of sitting together
         //    (measured: the slowest tiles were heavy ones sharing an SM with other heavy ones, +12 % over the model).
         std::stable_sort(tiles.begin(), tiles.end(), [](const int4& a, const int4& b) { return a.y < b.y; });
         if (warps_per_block > 0 && (int)tiles.size() > warps_per_block) {
