@@ -647,15 +647,23 @@ struct JacobiTB {
         // of the strip has a blocked neighbour) or the neighbour-free body ("solid": the strip is wholly
         // inside a circle there, with `depth` rows of margin for the rows in flight)
         std::vector<int> pre((size_t)nstrips * (nu + 1), 0), pres((size_t)nstrips * (nu + 1), 0);
-        std::vector<char> mark(nu);
-        for (int st_ = 0; st_ < nstrips; ++st_) {
-            const int c0 = st_ * pitch - hx - 1, c1 = st_ * pitch - hx + SW + 1;   // columns whose masks the strip reads
-            std::fill(mark.begin(), mark.end(), 0);
-            for (int pass = 0; pass < 2; ++pass) {           // pass 0: heavy rows, pass 1: solid rows override
-                for (int k = 0; k < nboxes; ++k) {
-                    const int* bx = boxes + 4 * k;
+        std::vector<char> marks((size_t)nstrips * nu, 0);
+        // boxes outside, strips inside: a box only visits the strips whose columns it can reach (a conservative
+        // range; the exact test follows), so the cost is per box-strip overlap, not boxes x strips
+        for (int pass = 0; pass < 2; ++pass) {               // pass 0: heavy rows, pass 1: solid rows override
+            for (int k = 0; k < nboxes; ++k) {
+                const int* bx = boxes + 4 * k;
+                const bool circle = bx[1] < bx[0];
+                if (!circle && pass == 1) continue;
+                const double xlo = circle ? (double)bx[0] - (double)(-1 - bx[1]) - 2.0 : (double)bx[0];
+                const double xhi = circle ? (double)bx[0] + (double)(-1 - bx[1]) + 2.0 : (double)bx[1];
+                const int s_lo = std::max(0, (int)std::floor((xlo + hx - SW - 1) / pitch) - 1);
+                const int s_hi = std::min(nstrips - 1, (int)std::ceil((xhi + hx + 1) / pitch) + 1);
+                for (int st_ = s_lo; st_ <= s_hi; ++st_) {
+                    const int c0 = st_ * pitch - hx - 1, c1 = st_ * pitch - hx + SW + 1;   // columns whose masks the strip reads
+                    char* mark = &marks[(size_t)st_ * nu];
                     int ya, yb;
-                    if (bx[1] < bx[0]) {
+                    if (circle) {
                         // circle (cx, -1 - r, cy, -): only the rows where it really crosses this strip's columns
                         const double cx = bx[0], r = (double)(-1 - bx[1]), cy = bx[2];
                         if (pass == 0) {
@@ -674,7 +682,7 @@ struct JacobiTB {
                             yb = std::min((int)std::floor(cy + hf), r1);
                         }
                     } else {
-                        if (pass == 1 || bx[1] <= c0 || bx[0] >= c1) continue;
+                        if (bx[1] <= c0 || bx[0] >= c1) continue;
                         ya = std::max(bx[2] - 1, r0);
                         yb = std::min(bx[3] + 1 + depth, r1);
                     }
@@ -686,6 +694,9 @@ struct JacobiTB {
                     }
                 }
             }
+        }
+        for (int st_ = 0; st_ < nstrips; ++st_) {
+            const char* mark = &marks[(size_t)st_ * nu];
             int* p = &pre[(size_t)st_ * (nu + 1)];
             int* q = &pres[(size_t)st_ * (nu + 1)];
             for (int u = 0; u < nu; ++u) { p[u + 1] = p[u] + (mark[u] == 1); q[u + 1] = q[u] + (mark[u] == 2); }
@@ -710,16 +721,44 @@ struct JacobiTB {
             return tiles;
         }
         // greedy cut of one strip under a cost limit: unit boundaries (ends) of its tiles
+        // (the planner runs on the host between the pre-projection launch and the first Jacobi launch; with moving
+        // obstacles it runs every step, so its cost matters: the search for a tile's end gallops out from the previous
+        // tile's length - tiles of a strip are of similar length - instead of bisecting the whole strip)
         auto cut_strip = [&](int st_, double limit, std::vector<int>* ends) {
-            int n = 0, ua = 0;
+            int n = 0, ua = 0, len = 0;
             while (ua < nu) {
-                int lo = ua + 1, hi = nu;                   // largest ub with cost <= limit (at least one unit)
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) / 2;
-                    if (cost(st_, ua, mid) <= limit) lo = mid; else hi = mid - 1;
+                // largest ub in (ua, nu] with cost(ua, ub) <= limit (at least one unit); cost is monotone in ub.
+                // invariant: cost(ua, good) <= limit (or good == ua + 1), cost(ua, bad) > limit (or bad == nu + 1)
+                auto fits = [&](int ub) { return cost(st_, ua, ub) <= limit; };
+                int good = ua + 1, bad = nu + 1;
+                const int probe = len > 0 ? std::min(nu, ua + len) : nu;
+                int step = std::max(1, len / 8);
+                if (probe > good) {
+                    if (fits(probe)) {
+                        good = probe;
+                        for (;;) {
+                            const int nx = std::min(nu, good + step);
+                            if (nx == good) break;
+                            if (fits(nx)) { good = nx; step *= 2; } else { bad = nx; break; }
+                        }
+                    } else {
+                        bad = probe;
+                        for (;;) {
+                            const int nx = std::max(ua + 1, bad - step);
+                            if (nx <= good) break;
+                            if (fits(nx)) { good = nx; break; }
+                            bad = nx;
+                            step *= 2;
+                        }
+                    }
                 }
-                if (ends) ends->push_back(lo);
-                ua = lo;
+                while (bad - good > 1) {
+                    const int mid = (good + bad) / 2;
+                    if (fits(mid)) good = mid; else bad = mid;
+                }
+                if (ends) ends->push_back(good);
+                len = good - ua;
+                ua = good;
                 ++n;
             }
             return n;
@@ -730,9 +769,11 @@ struct JacobiTB {
             return n;
         };
         // 1. the smallest common limit that needs no more tiles than there are resident warps
-        double lo = 0.0, hi = 0.0;
-        for (int st_ = 0; st_ < nstrips; ++st_) hi = std::max(hi, cost(st_, 0, nu));
-        for (int it = 0; it < 24; ++it) {
+        //    (bisection down to half a row; it starts from the perfect-packing bound, which no cut can beat)
+        double lo = 0.0, hi = 0.0, sum = 0.0;
+        for (int st_ = 0; st_ < nstrips; ++st_) { const double c = cost(st_, 0, nu); hi = std::max(hi, c); sum += c; }
+        lo = std::min(hi, sum / max_tiles);
+        for (int it = 0; it < 24 && hi - lo > 0.5; ++it) {
             const double mid = 0.5 * (lo + hi);
             if (count_all(mid) <= max_tiles) hi = mid; else lo = mid;
         }
@@ -742,8 +783,9 @@ struct JacobiTB {
         std::vector<int> k(nstrips);
         std::vector<double> lim(nstrips);
         auto tighten = [&](int st_) {                       // smallest limit that cuts strip st_ into <= k[st_] tiles
-            double a = 0.0, b = lim[st_];
-            for (int it = 0; it < 20; ++it) {
+            // k tiles cannot all cost less than the strip's cost shared out evenly (less the one warm-up it counts)
+            double a = std::max(0.0, (cost(st_, 0, nu) - warm * kappa) / k[st_]), b = lim[st_];
+            for (int it = 0; it < 20 && b - a > 0.5; ++it) {
                 const double mid = 0.5 * (a + b);
                 if (cut_strip(st_, mid, nullptr) <= k[st_]) b = mid; else a = mid;
             }
