@@ -560,14 +560,19 @@ int phase_solver(natrix_sim* s) {
     float* p = s->p[s->pr];
     if (s->p_is_zero) CU(cudaMemsetAsync(p, 0, (size_t)g.w * g.hl * sizeof(float), s->st));
     s->p_is_zero = false;
+    // the tiled smoother ping-pongs between the two pressure buffers: whichever holds the result becomes PRESSURE_READ
+    float* other = s->p[1 - s->pr];
+    int n;
     if (s->solver == 1) {
-        for (int k = 0; k < s->iterations; ++k)
-            s->launches += launch_sor_sweep(p, s->div, s->nbm, g.w, g.hl, (float)(s->sor_omega_milli * 1e-3), s->st);
+        n = launch_sor_sweeps(&p, &other, s->div, s->nbm, g.w, g.hl, (float)(s->sor_omega_milli * 1e-3), s->iterations, s->st);
     } else {
         if (!s->mg) s->mg = multigrid_create(g.w, g.hl);
         if (!s->mg) return fail(NATRIX_ERR_CUDA, "multigrid: out of device memory");
-        s->launches += multigrid_solve(s->mg, p, s->div, s->obs, s->nbm, s->iterations, s->mg_smooth, s->st);
+        n = multigrid_solve(s->mg, &p, &other, s->div, s->obs, s->nbm, s->iterations, s->mg_smooth, s->st);
     }
+    if (n < 0) return fail(NATRIX_ERR_CUDA, std::string("solver launch: ") + cudaGetErrorString(cudaGetLastError()));
+    s->launches += n;
+    if (p != s->p[s->pr]) s->pr = 1 - s->pr;
     CU(cudaGetLastError());
     return 0;
 }

@@ -93,13 +93,18 @@ int launch_add_circles(uint8_t* obs, Geom g, int r0, int r1, const float* sxyr, 
 // ---- opt-in solvers that are not reference behaviour (solvers.cu); full grids only
 // one red-black SOR sweep (both colours) in place on p; returns the kernels launched
 int launch_sor_sweep(float* p, const float* rhs, const uint8_t* mask, int w, int h, float omega, cudaStream_t st);
+// `sweeps` sweeps, up to 4 per launch in shared-memory tiles: every launch reads *p and writes *scratch and swaps the two,
+// so on return *p holds the result (NATRIX_SOR_BLOCK=0 or a null *scratch: the in-place one-colour kernels).  -1 on error.
+int launch_sor_sweeps(float** p, float** scratch, const float* rhs, const uint8_t* mask, int w, int h, float omega, int sweeps,
+                      cudaStream_t st);
 struct Multigrid;
 Multigrid* multigrid_create(int w, int h);        // nullptr when device memory ran out
 void multigrid_destroy(Multigrid* mg);
 int multigrid_levels(const Multigrid* mg);
-// `cycles` V(nu, nu) cycles with a red-black Gauss-Seidel smoother on the full grid's (p, rhs); obs / mask are the
-// step's obstacle bytes and blocked-neighbour mask.  Returns the kernels launched.
-int multigrid_solve(Multigrid* mg, float* p, const float* rhs, const uint8_t* obs, const uint8_t* mask, int cycles, int nu,
-                    cudaStream_t st);
+// `cycles` V(nu, nu) cycles with a red-black Gauss-Seidel smoother on the full grid's (*p, rhs); *p / *scratch are the two
+// pressure buffers (on return *p holds the result); obs / mask are the step's obstacle bytes and blocked-neighbour mask.
+// Returns the kernels launched, -1 on a launch error.
+int multigrid_solve(Multigrid* mg, float** p, float** scratch, const float* rhs, const uint8_t* obs, const uint8_t* mask,
+                    int cycles, int nu, cudaStream_t st);
 
 }  // namespace natrix
