@@ -1012,6 +1012,7 @@ int natrix_step_phase(natrix_sim* s, int phase, float dt, int sweeps) {
     case 1: return phase_forces(s, dt);
     case 2:
         NEED(sweeps > 0, "sweeps must be positive");
+        NEED(s->solver == 0, "the SOR / multigrid solvers are driven by natrix_step on a full grid, not phase by phase");
         if (s->first_block) stamp(s, ST_JACOBI);     // first block of the step: the stage spans all blocks + exchanges
         s->first_block = false;
         return phase_jacobi(s, sweeps);
