@@ -192,9 +192,13 @@ k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, fl
         // ---- stage 0: advect row ly (ref: shader.AdvectVelocity.comp:27-50).  All 4 cells are traced
         // without branching (16 independent gathers in flight); solid cells are zeroed afterwards.
         if (!PIPE) issue_row(ly);
+        // (finished for all four cells and selected afterwards: a branch per cell costs more than the mixes of a solid cell)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            An[j] = (g_valid && !((g_ow >> (8 * j)) & 0xffu)) ? gather_finish(G[j], prm.diss) : make_float2(0.0f, 0.0f);
+        for (int j = 0; j < 4; ++j) {
+            const float2 fin = gather_finish(G[j], prm.diss);
+            const bool keep = g_valid && !((g_ow >> (8 * j)) & 0xffu);
+            An[j] = make_float2(keep ? fin.x : 0.0f, keep ? fin.y : 0.0f);
+        }
         if (PIPE) issue_row(ly + 1);
 
         // ---- stage 1: vorticity of row r1 = ly-1 (ref: shader.CalcVorticity.comp:20-26)
@@ -275,32 +279,30 @@ k_preproject(const float2* __restrict__ vin, const uint8_t* __restrict__ obs, fl
             const uint32_t oM = *reinterpret_cast<const uint32_t*>(obs + lin(g, xc0, rd));
             const uint32_t oB = *reinterpret_cast<const uint32_t*>(obs + lin(g, xc0, max(gd - 1, 0) - g.y0));
             const uint32_t oT = *reinterpret_cast<const uint32_t*>(obs + lin(g, xc0, min(gd + 1, g.hg - 1) - g.y0));
-            const uint32_t oLw = __shfl_sync(FULL, oM, lane_l), oRw = __shfl_sync(FULL, oM, lane_r);
-            const uint32_t oL = edge_l ? (oM & 0xffu) : (oLw >> 24);          // obstacle byte of column xa-1
-            const uint32_t oR = edge_r ? (oM >> 24) : (oRw & 0xffu);          // obstacle byte of column xa+4
+            // solid flags of the 4 cells as one word, bit 0 of each byte (obstacle bytes are 0, 1 or 2; the bit that
+            // the shift drags in from the next byte lands on bit 7 and is masked off)
+            const uint32_t ONES = 0x01010101u;
+            const uint32_t sM = (oM | (oM >> 1)) & ONES, sB4 = (oB | (oB >> 1)) & ONES, sT4 = (oT | (oT >> 1)) & ONES;
+            const uint32_t sLw = __shfl_sync(FULL, sM, lane_l), sRw = __shfl_sync(FULL, sM, lane_r);
+            const uint32_t sl0 = edge_l ? (sM & 1u) : (sLw >> 24);            // solid flag of column xa-1 (the cell itself at the grid's edge)
+            const uint32_t sr3 = edge_r ? (sM >> 24) : (sRw & 1u);            // ... of column xa+4
+            const uint32_t sL4 = (sM << 8) | sl0, sR4 = (sM >> 8) | (sr3 << 24);
             const float lx = bitsel(F1[0].x, __shfl_sync(FULL, F1[3].x, lane_l), edge_l);
             const float rx = bitsel(F1[3].x, __shfl_sync(FULL, F1[0].x, lane_r), edge_r);
             float dv[4];
-            uint32_t mword = 0u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const bool sL = (j > 0 ? (oM >> (8 * (j - 1))) & 0xffu : oL) != 0u;
-                const bool sR = (j < 3 ? (oM >> (8 * (j + 1))) & 0xffu : oR) != 0u;
-                const bool sB = ((oB >> (8 * j)) & 0xffu) != 0u;
-                const bool sT = ((oT >> (8 * j)) & 0xffu) != 0u;
-                const float x1 = sL ? 0.0f : (j > 0 ? F1[j - 1].x : lx);
-                const float x2 = sR ? 0.0f : (j < 3 ? F1[j + 1].x : rx);
-                const float y1 = sB ? 0.0f : F0[j].y;
-                const float y2 = sT ? 0.0f : Fn[j].y;
+                const float x1 = (sL4 & (1u << (8 * j))) ? 0.0f : (j > 0 ? F1[j - 1].x : lx);
+                const float x2 = (sR4 & (1u << (8 * j))) ? 0.0f : (j < 3 ? F1[j + 1].x : rx);
+                const float y1 = (sB4 & (1u << (8 * j))) ? 0.0f : F0[j].y;
+                const float y2 = (sT4 & (1u << (8 * j))) ? 0.0f : Fn[j].y;
                 dv[j] = 0.5f * ((x2 - x1) + (y2 - y1));
-                const int x = xa + j;
-                uint32_t m = 0u;
-                if (sL || x == 0) m |= NB_L;
-                if (sR || x == g.w - 1) m |= NB_R;
-                if (sB || gd == 0) m |= NB_B;
-                if (sT || gd == g.hg - 1) m |= NB_T;
-                mword |= m << (8 * j);
             }
+            // blocked-neighbour mask: the solid flags moved to their bit, plus the grid's edges
+            uint32_t mword = sL4 | (sR4 << 1) | (sB4 << 2) | (sT4 << 3);
+            mword |= (edge_l & (uint32_t)NB_L) | (edge_r & ((uint32_t)NB_R << 24));
+            if (gd == 0) mword |= ONES * NB_B;
+            if (gd == g.hg - 1) mword |= ONES * NB_T;
             // the scaled copy the Jacobi kernels read (common.cuh NB_RAW): 0.25 b, exact for every b but a non-zero
             // |b| < 2^-124 - those cells keep b and carry the NB_RAW bit
             const float2 q = make_float2(0.25f, 0.25f), four = make_float2(4.0f, 4.0f);
