@@ -202,3 +202,28 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert cb["cores"] >= 1 and cb["value"] == d["value"] and "demo-640x360" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
+
+
+def test_bench_roofline_reads_the_committed_ncu_captures():
+    """bench.py turns profiles/kernel_traffic.json (ncu DRAM bytes per cell of the captured kernels) into the physical
+    roofline of its JSON line: the file must parse, name the kernels the bench asks for, and hold sane per-cell bytes."""
+    import importlib.util
+    import json
+
+    from conftest import ROOT
+
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    data = json.loads((ROOT / "profiles" / "kernel_traffic.json").read_text())
+    assert data["captures"] and all(c["dram_bytes_per_cell_per_launch"] > 0 for c in data["captures"])
+    big = bench.ncu_capture_for("k_jacobi_tb", 32768 * 4096)
+    mid = bench.ncu_capture_for("k_jacobi_tb", 4096 * 4096)
+    assert big["cells"] == 32768 * 4096 and mid["cells"] == 4096 * 4096
+    # a launch of the temporally blocked kernel must move at least 13 B per cell (p, div4, mask in; p out) minus what
+    # the 126 MB L2 keeps at 4096^2, and not much more than that
+    assert 13.0 <= big["dram_bytes_per_cell_per_launch"] < 18.0
+    assert 9.0 <= mid["dram_bytes_per_cell_per_launch"] < 18.0
+    assert 0.0 < big["sm_active_over_elapsed"] <= 1.0 and 0.0 < big["issue_active_pct"] <= 100.0
+    assert bench.ncu_capture_for("k_preproject", 32768 * 4096)["dram_bytes_per_cell_per_launch"] >= 26.0
+    assert bench.ncu_capture_for("k_no_such_kernel", 1) is None
