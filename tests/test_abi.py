@@ -76,3 +76,26 @@ def test_product_never_imports_the_oracle():
     for path in (ROOT / "natrix_b200" / "csrc").glob("*"):
         if path.suffix in (".cu", ".cuh", ".h"):
             assert "#include \"../../oracle" not in path.read_text()
+
+
+def test_no_kernel_uses_the_predicate_output_of_vimnmx_relu():
+    """Found the hard way: when the result of __vimin_s32_relu(v, m) is later compared with m, ptxas 12.9
+    folds the compare into VIMNMX.RELU's predicate output - and that predicate came out true for every cell on B200 (a
+    reference-order advect kernel wrote all zeros).  The shipped kernels only use the value form (predicates PT, PT);
+    this scan keeps it that way.  Also: sm_100a is the only architecture in the library."""
+    import re
+    import shutil
+    import subprocess
+
+    import pytest
+
+    from natrix_b200 import _lib as L
+
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump is not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", str(L.LIB_PATH)], capture_output=True, text=True, timeout=600).stdout
+    assert set(re.findall(r"arch = (sm_\w+)", sass)) == {"sm_100a"}
+    forms = set(re.findall(r"VIMNMX\.RELU\s+R\d+, (\w+), (\w+)", sass))
+    assert forms, "the fused pre-projection kernel clamps its gather corners with VIMNMX.RELU"
+    assert forms == {("PT", "PT")}, forms
+    assert "UTMALDG" in sass and "FFMA2" in sass          # TMA bulk tensor loads, 2-wide fp32: the Blackwell paths are in
